@@ -1,0 +1,49 @@
+"""CPU: the oracle restatement against the golden vectors produced by the unmodified reference."""
+import pytest
+import torch
+
+import golden_util
+import paramgen
+from oracle import refid_oracle as O
+
+
+@pytest.mark.parametrize("case", list(golden_util.CASES))
+def test_oracle_matches_reference_golden(case):
+    B, T, H, W, ic, ec, x5d = golden_util.CASES[case]
+    gold = golden_util.load(case)
+    shapes = O.param_shapes(ic, ec)
+    assert sorted(shapes) == gold["names"], "parameter inventory differs from the reference state_dict"
+    P = paramgen.make_params(shapes, seed=0)
+    x, ev, gt = paramgen.make_inputs(B, T, H, W, ic, ec, x5d=x5d)
+    torch.set_num_threads(8)
+    out, loss, grads = O.loss_and_grads(P, x, ev, gt)
+    assert out.shape == gold["out"].shape
+    assert (out - gold["out"]).abs().max().item() < 2e-5
+    assert abs(loss.item() - gold["loss"]) < 1e-6
+    assert sorted(O.dead_params(shapes)) == sorted(gold["dead"])
+    bad = golden_util.check_grads(grads, gold, rtol_norm=1e-3, atol_rel_samples=1e-2)
+    assert not bad, bad[:5]
+
+
+def test_param_count():
+    n = sum(int(torch.tensor(s).prod()) for s in O.param_shapes(26, 2).values())
+    assert n == 15928355
+    assert len(O.param_shapes(26, 2)) == 183
+
+
+def test_aliasing_quirk_matters():
+    """Fact 1: the forward sweep must see the frame-0 backward state for every frame. A 'fixed' variant
+    (per-frame backward state) must give a different answer, otherwise the test inputs cannot see the quirk."""
+    shapes = O.param_shapes(6, 2)
+    P = paramgen.make_params(shapes, seed=0)
+    x, ev, _ = paramgen.make_inputs(1, 3, 32, 32, 6, 2)
+    a = O.forward(P, x, ev)
+    b = O.forward(P, x, ev.flip(1))
+    assert (a - b.flip(1)).abs().max() > 1e-3
+
+
+def test_psnr_restatement():
+    a = torch.rand(3, 16, 16)
+    b = (a + 0.01).clamp(0, 1)
+    p = O.psnr_uint8(O.tensor2img_uint8(a), O.tensor2img_uint8(b))
+    assert 35 < p < 45
