@@ -1,0 +1,38 @@
+"""ctypes binding of librefid_b200.so (the C ABI declared in include/refid_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "librefid_b200.so")
+_lib = None
+
+c_void_p, c_int, c_long, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_PATH):
+            raise RuntimeError(
+                f"{_PATH} not found: build it with `python -m refid_b200.build` (nvcc, sm_100a). "
+                "refid_b200 has no CPU or PyTorch fallback.")
+        _lib = ctypes.CDLL(_PATH)
+        _lib.refid_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().refid_last_error().decode()}")
+
+
+def ptr(t):
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def abort_flag():
+    v = ctypes.c_uint(0)
+    check(lib().refid_abort_flag(ctypes.byref(v)), "refid_abort_flag")
+    return v.value

@@ -1,0 +1,89 @@
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace refid {
+
+static thread_local char g_err[1024] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+
+int read_and_clear_abort_flag(cudaStream_t stream, unsigned int* out) {
+  unsigned int v = 0, z = 0;
+  REFID_CUDA_CHECK(cudaStreamSynchronize(stream));
+  REFID_CUDA_CHECK(cudaMemcpyFromSymbol(&v, g_abort_flag, sizeof(v)));
+  if (v) REFID_CUDA_CHECK(cudaMemcpyToSymbol(g_abort_flag, &z, sizeof(z)));
+  *out = v;
+  return 0;
+}
+
+// cuTensorMapEncodeTiled is fetched through the runtime so the library has no link-time libcuda dependency.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
+  if (inner_bytes == 128) return CU_TENSOR_MAP_SWIZZLE_128B;
+  if (inner_bytes == 64) return CU_TENSOR_MAP_SWIZZLE_64B;
+  if (inner_bytes == 32) return CU_TENSOR_MAP_SWIZZLE_32B;
+  return CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int pitch, int C, int y0, int x0, int step,
+                 int boxC, int TW, int TH, int TN) {
+  EncodeTiledFn enc = get_encode();
+  REFID_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  REFID_REQUIRE(boxC == 64 || boxC == 32, "make_act_map: boxC must be 32 or 64 (got %d)", boxC);
+  REFID_REQUIRE(C % boxC == 0, "make_act_map: C=%d not a multiple of boxC=%d", C, boxC);
+  const int Ws = (W - x0 + step - 1) / step, Hs = (H - y0 + step - 1) / step;
+  const char* b = static_cast<const char*>(base) + ((size_t)y0 * W + x0) * pitch * 2;
+  REFID_REQUIRE((reinterpret_cast<uintptr_t>(b) & 15) == 0, "make_act_map: base not 16B aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * 2 * step, (cuuint64_t)W * pitch * 2 * step, (cuuint64_t)H * W * pitch * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(boxC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REFID_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: %d (N%d H%d W%d C%d pitch%d step%d box %d,%d,%d,%d)",
+                (int)r, N, H, W, C, pitch, step, boxC, TW, TH, TN);
+  return 0;
+}
+
+int make_mat_map(CUtensorMap* m, const void* base, long rows, long cols, int boxCols, int boxRows) {
+  EncodeTiledFn enc = get_encode();
+  REFID_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  REFID_REQUIRE(boxCols == 64 || boxCols == 32, "make_mat_map: boxCols must be 32 or 64");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)boxCols, (cuuint32_t)boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(boxCols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REFID_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(mat) failed: %d (rows %ld cols %ld box %d,%d)", (int)r, rows,
+                cols, boxCols, boxRows);
+  return 0;
+}
+
+}  // namespace refid

@@ -1,0 +1,226 @@
+#include "convop.cuh"
+
+#include <string.h>
+
+namespace refid {
+
+namespace {
+
+struct TapTable {
+  int n;
+  int dy[kMaxTaps], dx[kMaxTaps], map[kMaxTaps];
+  int parity_mode;
+  int grid_div;  // output grid = input / grid_div
+};
+
+// For the stride-2 4x4 conv (pad 1): input row = 2*y + k - 1.
+//   forward tap k -> parity view (k+1)&1, offset floor((k-1)/2) in that view.
+//   data-gradient for output parity q (row 2*i+q): the two contributing kernel rows and the dY offsets:
+//     q=0: k=1 (dY row i), k=3 (dY row i-1);  q=1: k=0 (dY row i+1), k=2 (dY row i).
+inline int down_fwd_off(int k) { return k == 0 ? -1 : (k == 3 ? 1 : 0); }
+inline int down_dgrad_off(int q, int a) { return q == 0 ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0); }
+
+int fill_taps(int kind, int parity, TapTable* t) {
+  memset(t, 0, sizeof(*t));
+  t->grid_div = 1;
+  switch (kind) {
+    case CK_3X3:
+      t->n = 9;
+      for (int i = 0; i < 9; ++i) {
+        t->dy[i] = i / 3 - 1;
+        t->dx[i] = i % 3 - 1;
+      }
+      return 0;
+    case CK_1X1:
+    case CK_UP2:
+      t->n = 1;
+      return 0;
+    case CK_DOWN4:
+      t->n = 16;
+      t->parity_mode = 1;
+      t->grid_div = 2;
+      for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) {
+          const int i = ky * 4 + kx;
+          t->dy[i] = down_fwd_off(ky);
+          t->dx[i] = down_fwd_off(kx);
+          t->map[i] = ((ky + 1) & 1) * 2 + ((kx + 1) & 1);
+        }
+      return 0;
+    case CK_DOWN4_DGRAD: {
+      t->n = 4;
+      const int py = parity >> 1, px = parity & 1;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          t->dy[a * 2 + b] = down_dgrad_off(py, a);
+          t->dx[a * 2 + b] = down_dgrad_off(px, b);
+        }
+      return 0;
+    }
+    case CK_UP2_DGRAD:
+      t->n = 4;
+      t->parity_mode = 1;
+      t->grid_div = 2;
+      for (int i = 0; i < 4; ++i) t->map[i] = i;
+      return 0;
+  }
+  set_error("fill_taps: unknown conv kind %d", kind);
+  return 1;
+}
+
+}  // namespace
+
+int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out) {
+  TapTable tt;
+  if (fill_taps(d.kind, d.parity, &tt)) return 1;
+  TapGemmParams& p = out->p;
+  memset(&p, 0, sizeof(p));
+  REFID_REQUIRE(d.nsrc == 1 || (d.nsrc == 2 && !tt.parity_mode), "build_conv: dual source not allowed with parity views");
+  REFID_REQUIRE(d.H % tt.grid_div == 0 && d.W % tt.grid_div == 0, "build_conv: H,W must be even for stride-2 ops");
+
+  int BK = 64;
+  for (int s = 0; s < d.nsrc; ++s) {
+    REFID_REQUIRE(d.src[s].C % 32 == 0, "build_conv: source channels %d not a multiple of 32", d.src[s].C);
+    if (d.src[s].C % 64) BK = 32;
+  }
+  int BN = 128;
+  for (int g = 0; g < ngroups; ++g) {
+    REFID_REQUIRE(groups[g].channels % 32 == 0, "build_conv: group channels %d not a multiple of 32", groups[g].channels);
+    while (groups[g].channels % BN) BN >>= 1;
+  }
+  const int gh = d.H / tt.grid_div, gw = d.W / tt.grid_div;
+  p.N = d.N;
+  p.H = gh;
+  p.W = gw;
+  pick_tile(d.N, gh, gw, &p.TW, &p.TH, &p.TN);
+  p.tiles_x = (gw + p.TW - 1) / p.TW;
+  p.tiles_y = (gh + p.TH - 1) / p.TH;
+  p.num_taps = tt.n;
+  p.parity_mode = tt.parity_mode;
+  for (int i = 0; i < tt.n; ++i) {
+    p.tap_dy[i] = (signed char)tt.dy[i];
+    p.tap_dx[i] = (signed char)tt.dx[i];
+    p.tap_map[i] = (signed char)tt.map[i];
+  }
+  p.nsrc = d.nsrc;
+  int ktot = 0;
+  for (int s = 0; s < d.nsrc; ++s) {
+    p.src_slabs[s] = d.src[s].C / BK;
+    ktot += d.src[s].C;
+  }
+  REFID_REQUIRE(ktot == d.w_cols, "build_conv: K mismatch: sources %d vs weight cols %d", ktot, d.w_cols);
+  if (tt.parity_mode) {
+    for (int par = 0; par < 4; ++par)
+      if (make_act_map(&p.tmA[par], d.src[0].ptr, d.N, d.H, d.W, d.src[0].pitch, d.src[0].C, par >> 1, par & 1, 2, BK, p.TW,
+                       p.TH, p.TN))
+        return 1;
+  } else {
+    for (int s = 0; s < d.nsrc; ++s)
+      if (make_act_map(&p.tmA[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, BK, p.TW, p.TH, p.TN))
+        return 1;
+  }
+  if (make_mat_map(&p.tmB, d.w, d.w_rows, d.w_cols, BK, BN)) return 1;
+  p.wrows_per_tap = d.wrows_per_tap;
+  p.w_row0 = d.w_row0;
+
+  // N blocks
+  int nb = 0;
+  const int reps = d.kind == CK_UP2 ? 4 : 1;
+  for (int r = 0; r < reps; ++r) {
+    for (int g = 0; g < ngroups; ++g) {
+      for (int c = 0; c < groups[g].channels; c += BN) {
+        REFID_REQUIRE(nb < kMaxNBlocks, "build_conv: too many N blocks");
+        EpiDesc e = groups[g].epi;
+        e.coff += c;
+        e.osy = e.osx = 1;
+        e.ooy = e.oox = 0;
+        e.OH = gh;
+        e.OW = gw;
+        if (d.kind == CK_UP2) {
+          e.osy = e.osx = 2;
+          e.ooy = r >> 1;
+          e.oox = r & 1;
+          e.OH = 2 * gh;
+          e.OW = 2 * gw;
+        } else if (d.kind == CK_DOWN4_DGRAD) {
+          e.osy = e.osx = 2;
+          e.ooy = d.parity >> 1;
+          e.oox = d.parity & 1;
+          e.OH = 2 * gh;
+          e.OW = 2 * gw;
+        }
+        p.epi[nb++] = e;
+      }
+    }
+  }
+  out->BN = BN;
+  out->BK = BK;
+  out->n_blocks = nb;
+  return 0;
+}
+
+int build_wgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
+  TapTable tt;
+  if (fill_taps(d.kind, d.parity, &tt)) return 1;
+  WgradParams& p = l->p;
+  memset(&p, 0, sizeof(p));
+  REFID_REQUIRE(d.nsrc == 1 || (d.nsrc == 2 && !tt.parity_mode), "build_wgrad: dual source not allowed with parity views");
+  int CB = 64;
+  int cp_total = 0;
+  for (int s = 0; s < d.nsrc; ++s) {
+    REFID_REQUIRE(d.src[s].C % 32 == 0, "build_wgrad: source channels %d", d.src[s].C);
+    if (d.src[s].C % 64) CB = 32;
+    cp_total += d.src[s].C;
+  }
+  REFID_REQUIRE(q.C % 32 == 0, "build_wgrad: q channels %d", q.C);
+  const int CBq = (q.C % 64) ? 32 : 64;
+  const int gh = d.H / tt.grid_div, gw = d.W / tt.grid_div;
+  p.N = d.N;
+  p.H = gh;
+  p.W = gw;
+  pick_tile(d.N, gh, gw, &p.TW, &p.TH, &p.TN);
+  p.tiles_x = (gw + p.TW - 1) / p.TW;
+  p.tiles_y = (gh + p.TH - 1) / p.TH;
+  p.num_tiles = p.tiles_x * p.tiles_y * ((d.N + p.TN - 1) / p.TN);
+  p.num_taps = tt.n;
+  p.parity_mode = tt.parity_mode;
+  for (int i = 0; i < tt.n; ++i) {
+    p.tap_dy[i] = (signed char)tt.dy[i];
+    p.tap_dx[i] = (signed char)tt.dx[i];
+    p.tap_map[i] = (signed char)tt.map[i];
+  }
+  p.nsrc = d.nsrc;
+  for (int s = 0; s < d.nsrc; ++s) p.src_blocks[s] = d.src[s].C / CB;
+  p.CB = CB;
+  p.CBq = CBq;
+  p.CQ = q.C;
+  p.BNq = q.C > 256 ? 256 : q.C;
+  REFID_REQUIRE(q.C % p.BNq == 0, "build_wgrad: q.C=%d", q.C);
+  const int bpt = 128 / CB;
+  const int total_blocks = tt.n * (cp_total / CB);
+  p.num_mtiles = (total_blocks + bpt - 1) / bpt;
+  p.mt_per_cta = 512 / p.BNq;
+  if (p.mt_per_cta > p.num_mtiles) p.mt_per_cta = p.num_mtiles;
+  p.total_rows = tt.n * cp_total;
+  p.out = outp;
+  if (tt.parity_mode) {
+    for (int par = 0; par < 4; ++par)
+      if (make_act_map(&p.tmP[par], d.src[0].ptr, d.N, d.H, d.W, d.src[0].pitch, d.src[0].C, par >> 1, par & 1, 2, CB, p.TW,
+                       p.TH, p.TN))
+        return 1;
+  } else {
+    for (int s = 0; s < d.nsrc; ++s)
+      if (make_act_map(&p.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, CB, p.TW, p.TH, p.TN))
+        return 1;
+  }
+  if (make_act_map(&p.tmQ, q.ptr, d.N, gh, gw, q.pitch, q.C, 0, 0, 1, CBq, p.TW, p.TH, p.TN)) return 1;
+  const int mt_groups = (p.num_mtiles + p.mt_per_cta - 1) / p.mt_per_cta;
+  const int ctas_per_chunk = mt_groups * (q.C / p.BNq);
+  int chunks = (296 + ctas_per_chunk - 1) / ctas_per_chunk;
+  if (chunks > p.num_tiles) chunks = p.num_tiles;
+  if (chunks < 1) chunks = 1;
+  l->pixel_chunks = chunks;
+  return 0;
+}
+
+}  // namespace refid

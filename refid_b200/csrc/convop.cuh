@@ -1,0 +1,58 @@
+// Host-side description of one convolution-shaped op and its lowering onto the tap-GEMM / wgrad kernels.
+#pragma once
+#include "tapgemm.cuh"
+#include "wgrad.cuh"
+
+namespace refid {
+
+enum ConvKind : int {
+  CK_3X3 = 0,          // 3x3 stride 1 pad 1 (also its data-gradient, with flipped/transposed packed weights)
+  CK_1X1 = 1,          // 1x1
+  CK_DOWN4 = 2,        // 4x4 stride 2 pad 1 forward: 16 taps over four stride-2 parity views; output grid H/2 x W/2
+  CK_UP2 = 3,          // ConvTranspose 2x2 stride 2 forward: one tap, N blocks = the 4 output parities (stride-2 scatter)
+  CK_DOWN4_DGRAD = 4,  // data-gradient of CK_DOWN4 for ONE output parity (4 taps on dY, stride-2 scatter); 4 launches
+  CK_UP2_DGRAD = 5     // data-gradient of CK_UP2: 2x2 stride-2 conv over dOut (4 taps, parity views); grid H/2 x W/2
+};
+
+struct ActSrc {
+  const __nv_bfloat16* ptr;
+  int C;      // channels read (K extent of this source)
+  int pitch;  // elements per pixel in memory
+};
+
+struct OutGroup {
+  int channels;  // output channels of this group (multiple of the chosen BN)
+  EpiDesc epi;   // out/out2/pre/.../bias/act/slope/C/coff set by caller; geometry fields filled by the lowering
+};
+
+struct ConvDesc {
+  int kind;
+  int parity;  // CK_DOWN4_DGRAD only: output parity py*2+px
+  ActSrc src[2];
+  int nsrc;
+  int N, H, W;  // spatial extent of the INPUT (src) tensors
+  const __nv_bfloat16* w;  // packed weights [w_rows][w_cols] bf16 (see weights.cuh for the layouts)
+  long w_rows;
+  int w_cols;
+  int wrows_per_tap;
+  int w_row0;
+};
+
+// Build params once (tensor maps are encoded here), launch many times.
+struct TapGemmLaunch {
+  TapGemmParams p;
+  int BN, BK, n_blocks;
+};
+int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out);
+inline int run_conv(TapGemmLaunch& l, cudaStream_t s) { return launch_tapgemm(l.p, l.BN, l.BK, l.n_blocks, s); }
+
+struct WgradLaunch {
+  WgradParams p;
+  int pixel_chunks;
+};
+// d describes the tapped operand P (kind, sources, taps); q is the un-shifted operand on the op's output grid.
+// out: fp32 [taps * sum(src C)][q.C], accumulated atomically.
+int build_wgrad(const ConvDesc& d, ActSrc q, float* out, WgradLaunch* l);
+inline int run_wgrad(WgradLaunch& l, cudaStream_t s) { return launch_wgrad(l.p, l.pixel_chunks, s); }
+
+}  // namespace refid

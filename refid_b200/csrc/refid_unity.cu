@@ -1,0 +1,7 @@
+// Single translation unit for librefid_b200.so (device symbols are shared without -rdc).
+#include <string.h>
+#include "common.cu"
+#include "tapgemm.cu"
+#include "wgrad.cu"
+#include "convop.cu"
+#include "api_test.cu"

@@ -1,0 +1,63 @@
+// Tap-GEMM: the im2col-free implicit-GEMM convolution engine (forward conv, data-gradient, transposed conv).
+//
+//   out[p, n] = epilogue( sum_{src} sum_{tap} sum_{c} A_src[ map_tap(p) ][c] * Wp[tap][n][k(src,c)] )
+//
+// p runs over a (N,H,W) grid of output-grid pixels in tiles of 128 (TN x TH x TW); map_tap is a spatial offset
+// (dy,dx) in the coordinate space of a TMA tensor map (plain NHWC view, or one of four stride-2 parity views), so
+// the 128 x BK activation tile of every tap is fetched by ONE cp.async.bulk.tensor with hardware zero padding.
+// tcgen05.mma (M=128, N=BN, K=16) accumulates in TMEM; 4 epilogue warps apply bias / residual / activation or
+// activation-derivative masks and write bf16 NHWC (optionally strided, e.g. stride-2 scatter of a transposed conv).
+#pragma once
+#include "common.cuh"
+
+namespace refid {
+
+constexpr int kMaxTaps = 16;
+constexpr int kMaxNBlocks = 8;
+
+enum ActKind : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2 };
+
+// Epilogue of one N block (all pointers share pixel mapping, channel pitch C and channel offset coff).
+//   a = acc + bias[n*bias_nstride + c] + pre + pre2
+//   if sv:  a *= act'(sv)      (LRELU: sv>0 ? 1 : slope, evaluated on the saved OUTPUT; GELU: on the saved PRE-activation)
+//   else :  if out_pre: out_pre = a;   a = act(a)
+//   out = a;  out_f32 += a;  out2 = a + post
+struct EpiDesc {
+  __nv_bfloat16* out;
+  __nv_bfloat16* out2;
+  __nv_bfloat16* out_pre;
+  float* out_f32;
+  const __nv_bfloat16* post;
+  const __nv_bfloat16* pre;
+  const __nv_bfloat16* pre2;
+  const __nv_bfloat16* sv;
+  const float* bias;
+  int bias_nstride;
+  int C, coff;
+  int osy, osx, ooy, oox, OH, OW;
+  int act;
+  float slope;
+};
+
+struct TapGemmParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  EpiDesc epi[kMaxNBlocks];
+  int num_taps;
+  signed char tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_map[kMaxTaps];
+  int wrows_per_tap;  // weight rows per tap (all N blocks)
+  int w_row0;         // first weight row of this launch
+  int nsrc;           // K-concatenated sources (1 or 2); src s uses tmA[s] unless parity_mode
+  int src_slabs[2];   // BK-slabs per source
+  int parity_mode;    // tap_map selects tmA (stride-2 views); single source
+  int TW, TH, TN, tiles_x, tiles_y;
+  int N, H, W;  // output-grid extent
+  int num_stages;
+};
+
+// Host: geometry helper -- picks TW x TH x TN = 128 for an (N,H,W) grid.
+void pick_tile(int N, int H, int W, int* TW, int* TH, int* TN);
+// Host: launch. grid = (tiles, n_blocks).
+int launch_tapgemm(TapGemmParams& p, int BN, int BK, int n_blocks, cudaStream_t stream);
+
+}  // namespace refid
