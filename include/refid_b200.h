@@ -1,0 +1,93 @@
+/* refid_b200 -- C ABI of the B200-native (sm_100a) backend for REFID's FinalBidirectionAttenfusion forward/backward.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference has no FFI of its own (it is pure
+ * PyTorch); the interface replaced is the Python call `net_g(x=lq, event=voxel)` made by the model wrappers
+ *   basicsr/models/twoImage_event_recurrent_model.py:276,324   (train / eval)
+ *   basicsr/models/Test_twoImage_event_recurrent_model.py:222  (test)
+ * on a module built by `define_network` (basicsr/models/archs/__init__.py:43-46) from
+ *   basicsr/models/archs/XXNet_final_attenfusion_arch.py:81-218 (FinalBidirectionAttenfusion),
+ * plus the backward pass autograd derives from it (`l_total.backward()`, twoImage_event_recurrent_model.py:303).
+ * The ctypes binding a maintainer adds is shown in INTEGRATION.md and shipped as refid_b200/engine.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer is allocated and owned by the caller (PyTorch);
+ *     the library borrows raw device pointers and never allocates device memory for data;
+ *   - every function returns 0 on success; on failure the message is available from refid_last_error()
+ *     (thread-local); no exceptions cross the ABI and nothing is silently "handled";
+ *   - all work is enqueued asynchronously on the caller's CUDA stream (cudaStream_t passed as void*);
+ *   - one handle may be used from any thread, one call at a time.
+ */
+#ifndef REFID_B200_H
+#define REFID_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct refid_engine* refid_handle;
+
+/* Constructor arguments of FinalBidirectionAttenfusion that change tensor shapes
+ * (XXNet_final_attenfusion_arch.py:90-92).  base_num_channels must be 32, num_encoders 3, num_block 1,
+ * num_residual_blocks 2, skip_type 'sum', norm None (the only configuration any shipped option file uses). */
+typedef struct {
+  int img_chn;
+  int ev_chn;
+  int out_chn; /* <= 8; 3 in every shipped config */
+  int base_num_channels;
+} refid_cfg;
+
+/* One entry of the flat fp32 parameter vector ("gradient layout") the engine consumes and whose gradient it
+ * produces.  kind: 0 conv3x3, 1 conv1x1, 2 conv4x4s2, 3 convT2x2s2, 4 head 5x5 (x-unrolled rows), 5 raw vector.
+ * Weight layout: [taps][R][Cc] fp32 at float offset w_off (conv: R = Cin (or padded 5*Cin), Cc = Cout, tap = ky*kw+kx;
+ * convT: R = Cout, Cc = Cin, tap = a*2+b).  Bias: nbias floats at b_off (-1: none). */
+typedef struct {
+  char key[96];
+  int kind, taps, R, Cc, nbias;
+  long w_off, b_off;
+} refid_param_entry;
+
+const char* refid_last_error(void);
+
+int refid_create(const refid_cfg* cfg, refid_handle* out);
+int refid_destroy(refid_handle h);
+
+int refid_num_param_entries(refid_handle h);
+int refid_param_entry_at(refid_handle h, int idx, refid_param_entry* out);
+long refid_flat_floats(refid_handle h);    /* length of the flat fp32 parameter / gradient vectors */
+size_t refid_wpack_bytes(refid_handle h);  /* persistent device buffer: fp32 master copy + bf16 UMMA-ready packs */
+
+/* Bytes of workspace (activations saved for backward, gradient pool) for one (B,T,H,W) problem. H, W % 8 == 0. */
+int refid_workspace_bytes(refid_handle h, int B, int T, int H, int W, int train, size_t* out);
+
+/* Build the launch plan (TMA tensor maps are encoded here) for fixed buffers.  grad_flat may be NULL when train == 0. */
+int refid_plan(refid_handle h, int B, int T, int H, int W, int train, void* workspace, void* wpack, float* grad_flat);
+
+/* flat (device, fp32, refid_flat_floats) -> master copy + bf16 packed weights inside wpack. */
+int refid_pack_weights(refid_handle h, const float* flat, void* stream);
+
+/* x: (B,img_chn,H,W) fp32 NCHW; event: (B,T,ev_chn,H,W) fp32; out: (B,T,out_chn,H,W) fp32.  Device pointers. */
+int refid_forward(refid_handle h, const float* x, const float* event, float* out, void* stream);
+/* grad_out: (B,T,out_chn,H,W) fp32.  Zeroes grad_flat, then accumulates d(loss)/d(flat) into it.
+ * Must follow a refid_forward on the same plan (train != 0). */
+int refid_backward(refid_handle h, const float* grad_out, void* stream);
+
+/* Introspection used by tests and profiling. */
+int refid_num_launches(refid_handle h, int* fwd, int* bwd);
+/* Device pointer + shape of a named intermediate activation (NHWC bf16, `pitch` channels per pixel). */
+int refid_debug_tensor(refid_handle h, const char* name, void** ptr, int* N, int* H, int* W, int* C, int* pitch);
+int refid_abort_flag(unsigned int* out); /* non-zero: a bounded mbarrier wait timed out inside a kernel */
+
+/* Single-kernel entry points (unit tests, ncu captures). */
+int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* in1, int C1, int N, int H, int W,
+                    const void* w, long w_rows, int w_cols, int wrows_per_tap, int w_row0, int Cout, const float* bias,
+                    const void* pre, const void* sv, int act, float slope, void* out, void* out_b, void* out2,
+                    const void* post, float* out_f32, void* stream);
+int refid_test_wgrad(int kind, const void* p0, int C0, const void* p1, int C1, int N, int H, int W, const void* q, int CQ,
+                     float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

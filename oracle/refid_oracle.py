@@ -155,7 +155,7 @@ def trunk(P, p: str, x: Tensor, h_prev: Optional[Tensor]) -> Tensor:
 
 
 def evr_layer(P, p: str, level: int, x: Tensor, y: Optional[Tensor], h_prev: Optional[Tensor],
-              h_other: Optional[Tensor]):
+              h_other: Optional[Tensor], rec=None, tag: str = ""):
     """SimpleRecurrentThenDownAttenfusionmodifiedConvLayer.forward (recurrent_sub_modules.py:270-296).
 
     The in-conv is a ConvLayer (conv + LReLU 0.2) followed by a second LReLU 0.2 (:279-285) => slope 0.04.
@@ -173,6 +173,11 @@ def evr_layer(P, p: str, level: int, x: Tensor, y: Optional[Tensor], h_prev: Opt
         o = _lrelu(F.conv2d(torch.cat((h, h_other), 1), P[p + ".fuse_two_dir.conv2d.weight"],
                             P[p + ".fuse_two_dir.conv2d.bias"]), 0.2)
     o = F.conv2d(o, P[p + ".down.weight"], None, stride=2, padding=1)
+    if rec is not None:
+        rec[tag + ".h"] = h.detach()
+        rec[tag + ".d"] = o.detach()
+        if level > 0:
+            rec[tag + ".u"] = u.detach()
     return o, h
 
 
@@ -200,7 +205,7 @@ def decoder_layer(P, p: str, x: Tensor, s_prev: Optional[Tensor]) -> Tensor:
 # ----------------------------------------------------------------------------------------------
 # the network
 # ----------------------------------------------------------------------------------------------
-def forward(P: Dict[str, Tensor], x: Tensor, event: Tensor) -> Tensor:
+def forward(P: Dict[str, Tensor], x: Tensor, event: Tensor, rec=None) -> Tensor:
     """FinalBidirectionAttenfusion.forward (XXNet_final_attenfusion_arch.py:130-218).
 
     x: (B,img_chn,H,W) or (B,t,c,H,W); event: (B,T,ev_chn,H,W); returns (B,T,out_chn,H,W).
@@ -218,12 +223,18 @@ def forward(P: Dict[str, Tensor], x: Tensor, event: Tensor) -> Tensor:
     for l in range(3):
         f = image_encoder_block(P, f"img_encoders.{l}", f)
         xb.append(f)
+    if rec is not None:
+        rec["head_img"] = head.detach()
+        rec["e_all"] = e.detach().transpose(0, 1).flatten(0, 1)  # t-major frames, as the engine stores them
+        for l in range(3):
+            rec[f"xb{l}"] = xb[l].detach()
 
     hb: List[Optional[Tensor]] = [None, None, None]
     for t in range(T - 1, -1, -1):
         cur = e[:, t]
         for l in range(3):
-            cur, hb[l] = evr_layer(P, f"encoders_backward.{l}", l, cur, xb[l - 1] if l > 0 else None, hb[l], None)
+            cur, hb[l] = evr_layer(P, f"encoders_backward.{l}", l, cur, xb[l - 1] if l > 0 else None, hb[l], None,
+                                   rec, f"b.t{t}.l{l}")
     # hb[l] now holds the final (frame 0) backward state: the only one the forward sweep ever sees.
 
     hf: List[Optional[Tensor]] = [None, None, None]
@@ -233,13 +244,20 @@ def forward(P: Dict[str, Tensor], x: Tensor, event: Tensor) -> Tensor:
         cur = e[:, t]
         skips = []
         for l in range(3):
-            cur, hf[l] = evr_layer(P, f"encoders_forward.{l}", l, cur, xb[l - 1] if l > 0 else None, hf[l], hb[l])
+            cur, hf[l] = evr_layer(P, f"encoders_forward.{l}", l, cur, xb[l - 1] if l > 0 else None, hf[l], hb[l],
+                                   rec, f"f.t{t}.l{l}")
             skips.append(cur)
         cur = res_block(P, "resblocks.0", cur + xb[2])
+        if rec is not None:
+            rec[f"f.t{t}.res0"] = cur.detach()
         cur = res_block(P, "resblocks.1", cur)
+        if rec is not None:
+            rec[f"f.t{t}.res1"] = cur.detach()
         for i in range(3):
             cur = decoder_layer(P, f"decoders.{i}", cur + skips[2 - i], sd[i])
             sd[i] = cur
+            if rec is not None:
+                rec[f"f.t{t}.dec{i}.h"] = cur.detach()
         outs.append(F.conv2d(cur + head, P["pred.conv2d.weight"], P["pred.conv2d.bias"], padding=1))
     return torch.stack(outs, 1)
 

@@ -176,11 +176,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, i
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// exact (erf) GELU and its derivative (reference: nn.GELU(), fusion_modules.py:271)
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
+  f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
+  uint4 a;
+  a.x = pack_bf16(f[0], f[1]); a.y = pack_bf16(f[2], f[3]); a.z = pack_bf16(f[4], f[5]); a.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = a;
 }
 #endif  // __CUDACC__
 

@@ -31,6 +31,10 @@ int fill_taps(int kind, int parity, TapTable* t) {
         t->dx[i] = i % 3 - 1;
       }
       return 0;
+    case CK_ROWS5:
+      t->n = 5;
+      for (int i = 0; i < 5; ++i) t->dy[i] = i - 2;
+      return 0;
     case CK_1X1:
     case CK_UP2:
       t->n = 1;

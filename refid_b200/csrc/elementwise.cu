@@ -1,0 +1,675 @@
+// Memory-bound kernels (see elementwise.cuh).  Every thread moves 16-byte vectors (8 bf16 channels); reductions are
+// done in registers -> warp shuffles -> shared memory -> one atomicAdd per block and channel.
+#include "elementwise.cuh"
+
+namespace refid {
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+inline unsigned blocks_for(long n, int per_block) {
+  long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+__device__ __forceinline__ float act_mask(float sv, int act, float slope) {
+  if (act == ACT_LRELU) return sv > 0.f ? 1.f : slope;
+  if (act == ACT_GELU) return gelu_grad_f(sv);
+  return 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// input / output-gradient layout conversion
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
+                                                        int T, int Cin, int H, int W, int Kp) {
+  const int G = Kp / 8;
+  const long total = (long)B * T * H * G * W;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    long r = idx / W;
+    const int g = (int)(r % G);
+    r /= G;
+    const int y = (int)(r % H);
+    const int n_out = (int)(r / H);
+    const int t = n_out / B, b = n_out % B;
+    const float* src = in + ((size_t)(b * T + t) * Cin) * H * W + (size_t)y * W;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = g * 8 + i;
+      const int kx = k / Cin, c = k - kx * Cin;
+      const int xx = x + kx - 2;
+      v[i] = (kx < 5 && xx >= 0 && xx < W) ? __ldg(src + (size_t)c * H * W + xx) : 0.f;
+    }
+    store8(out + (((size_t)n_out * H + y) * W + x) * Kp + g * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads) k_gout_pack(const float* __restrict__ gout, __nv_bfloat16* __restrict__ out, int B,
+                                                          int T, int Cv, int H, int W) {
+  const long total = (long)B * T * H * W;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long hw = (long)H * W;
+    const long pix = idx % hw;
+    const int n_out = (int)(idx / hw);
+    const int t = n_out / B, b = n_out % B;
+    const float* src = gout + ((size_t)(b * T + t) * Cv) * hw + pix;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < Cv && c < 8; ++c) v[c] = __ldg(src + (size_t)c * hw);
+    __nv_bfloat16* o = out + (size_t)idx * 32;
+    store8(o, v);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(o)[1] = z;
+    reinterpret_cast<uint4*>(o)[2] = z;
+    reinterpret_cast<uint4*>(o)[3] = z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sum (bias gradients)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads) k_colsum(const __nv_bfloat16* __restrict__ in, long rows, int C,
+                                                       float* __restrict__ out) {
+  __shared__ float red[kEwThreads][9];
+  const int G = C / 8;                 // vector groups per row (4..32)
+  const int lanes = kEwThreads / G;    // row lanes per block
+  const int g = threadIdx.x % G, rl = threadIdx.x / G;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < lanes) {
+    for (long r = (long)blockIdx.x * lanes + rl; r < rows; r += (long)gridDim.x * lanes) {
+      float v[8];
+      load8(in + (size_t)r * C + g * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x, gg = c / 8, i = c % 8;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * G + gg][i];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// masked accumulate
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads) k_addmask(const AddMaskArgs p) {
+  const long n8 = p.n / 8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float t[8];
+    if (p.a) {
+      load8(p.a + i * 8, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += t[k];
+    }
+    if (p.b) {
+      load8(p.b + i * 8, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += t[k];
+    }
+    if (p.f) {
+      const float4 f0 = reinterpret_cast<const float4*>(p.f + i * 8)[0], f1 = reinterpret_cast<const float4*>(p.f + i * 8)[1];
+      v[0] += f0.x; v[1] += f0.y; v[2] += f0.z; v[3] += f0.w;
+      v[4] += f1.x; v[5] += f1.y; v[6] += f1.z; v[7] += f1.w;
+    }
+    if (p.dstf) {
+      float4* o = reinterpret_cast<float4*>(p.dstf + i * 8);
+      float4 f0 = o[0], f1 = o[1];
+      f0.x += v[0]; f0.y += v[1]; f0.z += v[2]; f0.w += v[3];
+      f1.x += v[4]; f1.y += v[5]; f1.z += v[6]; f1.w += v[7];
+      o[0] = f0;
+      o[1] = f1;
+    }
+    if (p.dst) {
+      if (p.dst_acc) {
+        load8(p.dst + i * 8, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += t[k];
+      }
+      if (p.sv) {
+        load8(p.sv + i * 8, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= act_mask(t[k], p.act, p.slope);
+      }
+      store8(p.dst + i * 8, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over 64 channels: 8 lanes per pixel, 8 channels per lane
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sum8lanes(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+__device__ __forceinline__ void ln_stats(const float* x, float& mu, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  mu = sum8lanes(s) * (1.f / 64.f);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) q += (x[k] - mu) * (x[k] - mu);
+  rstd = rsqrtf(sum8lanes(q) * (1.f / 64.f) + 1e-6f);
+}
+
+__global__ void __launch_bounds__(kEwThreads) k_ln_fwd(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                       long npix) {
+  const long nvec = npix * 8;
+  const long iters = (nvec + (long)gridDim.x * blockDim.x - 1) / ((long)gridDim.x * blockDim.x);
+  for (long it = 0; it < iters; ++it) {  // uniform trip count: shuffles need whole warps
+    const long i = it * gridDim.x * blockDim.x + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i < nvec;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) load8(x + i * 8, v);
+    float mu, rstd;
+    ln_stats(v, mu, rstd);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (v[k] - mu) * rstd;
+    if (ok) store8(y + i * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads) k_ln_bwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
+                                                       const __nv_bfloat16* __restrict__ add, __nv_bfloat16* dst, int dst_acc,
+                                                       float* dstf, long npix) {
+  const long nvec = npix * 8;
+  const long iters = (nvec + (long)gridDim.x * blockDim.x - 1) / ((long)gridDim.x * blockDim.x);
+  for (long it = 0; it < iters; ++it) {
+    const long i = it * gridDim.x * blockDim.x + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = i < nvec;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0}, g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) {
+      load8(x + i * 8, v);
+      load8(gy + i * 8, g);
+    }
+    float mu, rstd;
+    ln_stats(v, mu, rstd);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (v[k] - mu) * rstd;  // xhat
+      sg += g[k];
+      sgx += g[k] * v[k];
+    }
+    sg = sum8lanes(sg) * (1.f / 64.f);
+    sgx = sum8lanes(sgx) * (1.f / 64.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = rstd * (g[k] - sg - v[k] * sgx);
+    if (!ok) continue;
+    float t[8];
+    if (add) {
+      load8(add + i * 8, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += t[k];
+    }
+    if (dstf) {
+      float4* o = reinterpret_cast<float4*>(dstf + i * 8);
+      float4 f0 = o[0], f1 = o[1];
+      f0.x += v[0]; f0.y += v[1]; f0.z += v[2]; f0.w += v[3];
+      f1.x += v[4]; f1.y += v[5]; f1.z += v[6]; f1.w += v[7];
+      o[0] = f0;
+      o[1] = f1;
+    }
+    if (dst) {
+      if (dst_acc) {
+        load8(dst + i * 8, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += t[k];
+      }
+      store8(dst + i * 8, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3 (C = 64): block = 32 pixels x 8 channel groups
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ d,
+                                                       __nv_bfloat16* __restrict__ g, float* pool, int N, int H, int W) {
+  __shared__ float sw[64 * 9 + 64];
+  __shared__ float spool[8][64];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) sw[64 * 9 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const long hw = (long)H * W, npix = (long)N * hw;
+  const long pix = (long)blockIdx.x * 32 + pl;
+  float gv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (pix < npix) {
+    const int n = (int)(pix / hw);
+    const int y = (int)((pix % hw) / W), x = (int)(pix % W);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = sw[64 * 9 + grp * 8 + k];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        float v[8];
+        load8(a + (((size_t)n * H + yy) * W + xx) * 64 + grp * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k] * sw[(grp * 8 + k) * 9 + ky * 3 + kx];
+      }
+    }
+    store8(d + (size_t)pix * 64 + grp * 8, acc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gv[k] = gelu_f(acc[k]);
+    store8(g + (size_t)pix * 64 + grp * 8, gv);
+  }
+  if (pool) {
+    const long first = (long)blockIdx.x * 32, last = min(first + 31, npix - 1);
+    if (first / hw == last / hw) {  // whole block inside one sample: block-level reduction
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 8);
+        gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 16);
+      }
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      if (lane < 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) spool[warp][lane * 8 + k] = gv[k];
+      }
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) s += spool[wq][threadIdx.x];
+        atomicAdd(pool + (first / hw) * 64 + threadIdx.x, s);
+      }
+    } else if (pix < npix) {
+      const int n = (int)(pix / hw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(pool + (size_t)n * 64 + grp * 8 + k, gv[k]);
+    }
+  }
+}
+
+constexpr int kDwBwdPix = 256;  // pixels per block in the backward kernel (8 per thread)
+
+__global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __restrict__ gd, const __nv_bfloat16* __restrict__ a,
+                                                       const float* __restrict__ w, __nv_bfloat16* __restrict__ ga, float* gw,
+                                                       float* gb, int N, int H, int W) {
+  __shared__ float sw[64 * 9];
+  __shared__ float sred[64 * 10];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 64 * 10; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const long hw = (long)H * W, npix = (long)N * hw;
+  float aw[8][9];
+  float ab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    ab[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) aw[k][t] = 0.f;
+  }
+  for (int j = 0; j < kDwBwdPix / 32; ++j) {
+    const long pix = (long)blockIdx.x * kDwBwdPix + j * 32 + pl;
+    if (pix >= npix) break;
+    const int n = (int)(pix / hw);
+    const int y = (int)((pix % hw) / W), x = (int)(pix % W);
+    float gc[8];
+    load8(gd + (size_t)pix * 64 + grp * 8, gc);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ab[k] += gc[k];
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        // weight gradient: a[p + off] * gd[p]
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          float v[8];
+          load8(a + (((size_t)n * H + yy) * W + xx) * 64 + grp * 8, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) aw[k][ky * 3 + kx] += v[k] * gc[k];
+        }
+        // data gradient: gd[p - off] * w[tap]
+        const int y2 = y - (ky - 1), x2 = x - (kx - 1);
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+          float v[8];
+          load8(gd + (((size_t)n * H + y2) * W + x2) * 64 + grp * 8, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += v[k] * sw[(grp * 8 + k) * 9 + ky * 3 + kx];
+        }
+      }
+    }
+    store8(ga + (size_t)pix * 64 + grp * 8, acc);
+  }
+  // reduce the 32 pixel lanes that share a channel group: lanes grp, grp+8, grp+16, grp+24 of each warp, then 8 warps
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float v = aw[k][t];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      aw[k][t] = v;
+    }
+    float v = ab[k];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    ab[k] = v;
+  }
+  if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&sred[(grp * 8 + k) * 9 + t], aw[k][t]);
+      atomicAdd(&sred[64 * 9 + grp * 8 + k], ab[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) atomicAdd(gw + i, sred[i]);
+  if (threadIdx.x < 64) atomicAdd(gb + threadIdx.x, sred[64 * 9 + threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// squeeze-excite MLP: one block of 64 threads per sample
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_se_fwd(const float* __restrict__ pool_sum, float inv_hw, SeParams p, float* s,
+                                               float* save_mean, float* save_z) {
+  __shared__ float m[64], z[32];
+  const int n = blockIdx.x, c = threadIdx.x;
+  m[c] = pool_sum[n * 64 + c] * inv_hw;
+  save_mean[n * 64 + c] = m[c];
+  __syncthreads();
+  if (c < 32) {
+    float acc = p.b1[c];
+    for (int i = 0; i < 64; ++i) acc += p.w1[c * 64 + i] * m[i];
+    z[c] = fmaxf(acc, 0.f);
+    save_z[n * 32 + c] = z[c];
+  }
+  __syncthreads();
+  float acc = p.b2[c];
+  for (int j = 0; j < 32; ++j) acc += p.w2[c * 32 + j] * z[j];
+  s[n * 64 + c] = 1.f / (1.f + __expf(-acc));
+}
+
+__global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, const float* __restrict__ s,
+                                               const float* __restrict__ save_mean, const float* __restrict__ save_z, float inv_hw,
+                                               SeParams p, float* gpool) {
+  __shared__ float gq[64], gz[32], m[64], z[32];
+  const int n = blockIdx.x, c = threadIdx.x;
+  const float sv = s[n * 64 + c];
+  gq[c] = gs[n * 64 + c] * sv * (1.f - sv);  // gradient at the pre-sigmoid logits
+  m[c] = save_mean[n * 64 + c];
+  if (c < 32) z[c] = save_z[n * 32 + c];
+  __syncthreads();
+  atomicAdd(p.gb2 + c, gq[c]);
+  for (int j = 0; j < 32; ++j) atomicAdd(p.gw2 + c * 32 + j, gq[c] * z[j]);
+  if (c < 32) {
+    float acc = 0.f;
+    for (int o = 0; o < 64; ++o) acc += p.w2[o * 32 + c] * gq[o];
+    gz[c] = z[c] > 0.f ? acc : 0.f;
+    atomicAdd(p.gb1 + c, gz[c]);
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int j = 0; j < 32; ++j) {
+    acc += p.w1[j * 64 + c] * gz[j];
+    atomicAdd(p.gw1 + j * 64 + c, gz[j] * m[c]);
+  }
+  gpool[n * 64 + c] = acc * inv_hw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel gating
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads) k_gate_fwd(const __nv_bfloat16* __restrict__ gi, const __nv_bfloat16* __restrict__ ge,
+                                                         const float* __restrict__ s, __nv_bfloat16* __restrict__ cs, int N, long hw) {
+  const long nvec = (long)N * hw * 8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i >> 3;
+    const int grp = (int)(i & 7);
+    const int n = (int)(pix / hw);
+    const float* sc = s + (size_t)n * 64 + grp * 8;
+    float a[8], b[8];
+    load8(gi + i * 8, a);
+    load8(ge + i * 8, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float f = __ldg(sc + k);
+      a[k] *= f;
+      b[k] *= f;
+    }
+    store8(cs + (size_t)pix * 128 + grp * 8, a);
+    store8(cs + (size_t)pix * 128 + 64 + grp * 8, b);
+  }
+}
+
+constexpr int kGatePix = 512;  // pixels per block in the reduction (16 per thread)
+
+__global__ void __launch_bounds__(kEwThreads) k_gate_bwd_reduce(const __nv_bfloat16* __restrict__ gcs,
+                                                                const __nv_bfloat16* __restrict__ gi,
+                                                                const __nv_bfloat16* __restrict__ ge, float* gs, long hw) {
+  __shared__ float sred[64];
+  if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < kGatePix / 32; ++j) {
+    const long p = (long)blockIdx.x * kGatePix + j * 32 + pl;
+    if (p >= hw) break;
+    const size_t pix = (size_t)n * hw + p;
+    float a[8], b[8], ga[8], gb[8];
+    load8(gi + pix * 64 + grp * 8, a);
+    load8(ge + pix * 64 + grp * 8, b);
+    load8(gcs + pix * 128 + grp * 8, ga);
+    load8(gcs + pix * 128 + 64 + grp * 8, gb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += a[k] * ga[k] + b[k] * gb[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+  }
+  if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&sred[grp * 8 + k], acc[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(gs + (size_t)n * 64 + threadIdx.x, sred[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kEwThreads) k_gate_bwd_apply(const __nv_bfloat16* __restrict__ gcs, const float* __restrict__ s,
+                                                               const float* __restrict__ gpool,
+                                                               const __nv_bfloat16* __restrict__ d_e, float* gi_f32,
+                                                               __nv_bfloat16* __restrict__ gz_de, int N, long hw) {
+  const long nvec = (long)N * hw * 8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i >> 3;
+    const int grp = (int)(i & 7);
+    const int n = (int)(pix / hw);
+    const float* sc = s + (size_t)n * 64 + grp * 8;
+    const float* gp = gpool + (size_t)n * 64 + grp * 8;
+    float ga[8], gb[8], d[8];
+    load8(gcs + (size_t)pix * 128 + grp * 8, ga);
+    load8(gcs + (size_t)pix * 128 + 64 + grp * 8, gb);
+    load8(d_e + i * 8, d);
+    float4* o = reinterpret_cast<float4*>(gi_f32 + i * 8);
+    float4 f0 = o[0], f1 = o[1];
+    float sk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sk[k] = __ldg(sc + k);
+    f0.x += ga[0] * sk[0]; f0.y += ga[1] * sk[1]; f0.z += ga[2] * sk[2]; f0.w += ga[3] * sk[3];
+    f1.x += ga[4] * sk[4]; f1.y += ga[5] * sk[5]; f1.z += ga[6] * sk[6]; f1.w += ga[7] * sk[7];
+    o[0] = f0;
+    o[1] = f1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gb[k] = (gb[k] * sk[k] + __ldg(gp + k)) * gelu_grad_f(d[k]);
+    store8(gz_de + i * 8, gb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight repacking
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ flat, __nv_bfloat16* __restrict__ wpack,
+                                                     const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  const long per_tap = (long)d.R * d.Cc;
+  const long total = per_tap * d.ntaps;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / per_tap);
+    const long r = i % per_tap;
+    long src;
+    if (d.transpose) {  // dst [t][Cc][R]
+      const int j = (int)(r / d.R), ii = (int)(r % d.R);
+      src = (long)d.tapmap[t] * per_tap + (long)ii * d.Cc + j;
+    } else {
+      src = (long)d.tapmap[t] * per_tap + r;
+    }
+    wpack[d.dst_off + i] = __float2bfloat16(flat[d.src_off + src]);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, int H, int W, int Kp, cudaStream_t s) {
+  REFID_REQUIRE(Kp % 32 == 0 && Kp >= 5 * Cin, "unroll5: Kp=%d too small for Cin=%d", Kp, Cin);
+  const long total = (long)B * T * H * W * (Kp / 8);
+  unsigned blocks = blocks_for(total, kEwThreads);
+  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  k_unroll5<<<blocks, kEwThreads, 0, s>>>(in, out, B, T, Cin, H, W, Kp);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gout_pack(const float* gout, __nv_bfloat16* out, int B, int T, int Cv, int H, int W, cudaStream_t s) {
+  REFID_REQUIRE(Cv <= 8, "gout_pack: out_chn %d > 8 unsupported", Cv);
+  const long total = (long)B * T * H * W;
+  unsigned blocks = blocks_for(total, kEwThreads);
+  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  k_gout_pack<<<blocks, kEwThreads, 0, s>>>(gout, out, B, T, Cv, H, W);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_colsum(const __nv_bfloat16* in, long rows, int C, float* out, cudaStream_t s) {
+  REFID_REQUIRE(C % 8 == 0 && C <= 256 && (kEwThreads % (C / 8)) == 0, "colsum: unsupported C=%d", C);
+  const int lanes = kEwThreads / (C / 8);
+  unsigned blocks = blocks_for(rows, lanes * 16);
+  if (blocks > 148u * 4u) blocks = 148u * 4u;
+  k_colsum<<<blocks, kEwThreads, 0, s>>>(in, rows, C, out);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_addmask(const AddMaskArgs& a, cudaStream_t s) {
+  REFID_REQUIRE(a.n % 8 == 0, "addmask: n=%ld not a multiple of 8", a.n);
+  unsigned blocks = blocks_for(a.n / 8, kEwThreads);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  k_addmask<<<blocks, kEwThreads, 0, s>>>(a);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s) {
+  unsigned blocks = blocks_for(npix * 8, kEwThreads);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  k_ln_fwd<<<blocks, kEwThreads, 0, s>>>(x, y, npix);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bfloat16* add, __nv_bfloat16* dst, int dst_acc,
+                  float* dstf, long npix, cudaStream_t s) {
+  unsigned blocks = blocks_for(npix * 8, kEwThreads);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  k_ln_bwd<<<blocks, kEwThreads, 0, s>>>(x, gy, add, dst, dst_acc, dstf, npix);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
+                  int N, int H, int W, cudaStream_t s) {
+  const long npix = (long)N * H * W;
+  k_dw_fwd<<<blocks_for(npix, 32), kEwThreads, 0, s>>>(a, w, bias, d, g, pool, N, H, W);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* w, __nv_bfloat16* ga, float* gw, float* gb,
+                  int N, int H, int W, cudaStream_t s) {
+  const long npix = (long)N * H * W;
+  k_dw_bwd<<<blocks_for(npix, kDwBwdPix), kEwThreads, 0, s>>>(gd, a, w, ga, gw, gb, N, H, W);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_se_fwd(const float* pool_sum, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
+                  cudaStream_t st) {
+  k_se_fwd<<<N, 64, 0, st>>>(pool_sum, inv_hw, p, s, save_mean, save_z);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const float* save_z, float inv_hw, SeParams p,
+                  float* gpool, int N, cudaStream_t st) {
+  k_se_bwd<<<N, 64, 0, st>>>(gs, s, save_mean, save_z, inv_hw, p, gpool);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const float* s, __nv_bfloat16* cs, int N, long hw,
+                    cudaStream_t st) {
+  unsigned blocks = blocks_for((long)N * hw * 8, kEwThreads);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  k_gate_fwd<<<blocks, kEwThreads, 0, st>>>(gi, ge, s, cs, N, hw);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gate_bwd_reduce(const __nv_bfloat16* gcs, const __nv_bfloat16* gi, const __nv_bfloat16* ge, float* gs, int N, long hw,
+                           cudaStream_t st) {
+  dim3 grid(blocks_for(hw, kGatePix), N);
+  k_gate_bwd_reduce<<<grid, kEwThreads, 0, st>>>(gcs, gi, ge, gs, hw);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gate_bwd_apply(const __nv_bfloat16* gcs, const float* s, const float* gpool, const __nv_bfloat16* d_e, float* gi_f32,
+                          __nv_bfloat16* gz_de, int N, long hw, cudaStream_t st) {
+  unsigned blocks = blocks_for((long)N * hw * 8, kEwThreads);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  k_gate_bwd_apply<<<blocks, kEwThreads, 0, st>>>(gcs, s, gpool, d_e, gi_f32, gz_de, N, hw);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_dev, int ndesc, long max_elems, cudaStream_t st) {
+  unsigned bx = blocks_for(max_elems, kEwThreads * 4);
+  if (bx > 1024u) bx = 1024u;
+  dim3 grid(bx, ndesc);
+  k_pack<<<grid, kEwThreads, 0, st>>>(flat, wpack, descs_dev);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace refid

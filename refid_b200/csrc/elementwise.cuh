@@ -1,0 +1,82 @@
+// Memory-bound kernels around the tap-GEMM engine: layout conversion of the network inputs / output gradient,
+// bias-gradient column sums, masked gradient accumulation, and the pieces of EGACA (event-guided adaptive channel
+// attention, reference basicsr/models/archs/fusion_modules.py:237-333) that are not 1x1 GEMMs: per-pixel LayerNorm,
+// depthwise 3x3 + GELU (+ global pooling), the squeeze-excite MLP and the channel gating.
+// All activations are NHWC bf16, 16-byte vectorised (8 channels per thread); statistics and parameters are fp32.
+#pragma once
+#include "tapgemm.cuh"
+
+namespace refid {
+
+// fp32 NCHW (frame n_in = b*T + t) -> bf16 NHWC [t*B + b][H][W][Kp], channel k = kx*Cin + c holds in[c][y][x+kx-2].
+int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, int H, int W, int Kp, cudaStream_t s);
+// fp32 (B,T,Cv,H,W) -> bf16 [t*B + b][H][W][32] (channels >= Cv zero).
+int launch_gout_pack(const float* gout, __nv_bfloat16* out, int B, int T, int Cv, int H, int W, cudaStream_t s);
+// out[c] += sum_rows in[row][c]   (bf16 [rows][C] contiguous, C % 8 == 0, C <= 256)
+int launch_colsum(const __nv_bfloat16* in, long rows, int C, float* out, cudaStream_t s);
+
+// dst = mask(sv) * ((dst_acc ? dst : 0) + a + b + f);   dstf += a + b + f (unmasked).  n = element count (% 8 == 0).
+struct AddMaskArgs {
+  const __nv_bfloat16* a;
+  const __nv_bfloat16* b;
+  const float* f;
+  const __nv_bfloat16* sv;
+  int act;
+  float slope;
+  __nv_bfloat16* dst;
+  int dst_acc;
+  float* dstf;
+  long n;
+};
+int launch_addmask(const AddMaskArgs& a, cudaStream_t s);
+
+// Per-pixel LayerNorm over C = 64 channels without affine (the affine is folded into the following 1x1 conv).
+int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s);
+// val = d(LN)/dx applied to gy;  dst = (dst_acc ? dst : 0) + add + val   or   dstf += val.
+int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bfloat16* add, __nv_bfloat16* dst, int dst_acc,
+                  float* dstf, long npix, cudaStream_t s);
+
+// Depthwise 3x3 (pad 1) over C = 64: d = dw(a) + bias (saved pre-activation), g = GELU(d); pool[n][c] += sum_pix g.
+int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
+                  int N, int H, int W, cudaStream_t s);
+// ga = dw^T(gd); gw[c][tap] += sum a[p+tap] gd[p]; gb[c] += sum gd[p].
+int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* w, __nv_bfloat16* ga, float* gw, float* gb,
+                  int N, int H, int W, cudaStream_t s);
+
+// Squeeze-excite MLP on the pooled event statistics: s = sigmoid(W2 relu(W1 mean + b1) + b2), C = 64, hidden 32.
+struct SeParams {
+  const float* w1;  // (32,64)
+  const float* b1;
+  const float* w2;  // (64,32)
+  const float* b2;
+  float* gw1;
+  float* gb1;
+  float* gw2;
+  float* gb2;
+};
+int launch_se_fwd(const float* pool_sum, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
+                  cudaStream_t st);
+// gpool[n][c] = inv_hw * dL/dmean[n][c]
+int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const float* save_z, float inv_hw, SeParams p,
+                  float* gpool, int N, cudaStream_t st);
+
+// cs[pix][0:64] = gi*s[n], cs[pix][64:128] = ge*s[n]
+int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const float* s, __nv_bfloat16* cs, int N, long hw,
+                    cudaStream_t st);
+// gs[n][c] += sum_pix gcs[:, c]*gi + gcs[:, 64+c]*ge
+int launch_gate_bwd_reduce(const __nv_bfloat16* gcs, const __nv_bfloat16* gi, const __nv_bfloat16* ge, float* gs, int N,
+                           long hw, cudaStream_t st);
+// gi_f32 += gcs[:, :64]*s ;  gz_de = (gcs[:, 64:]*s + gpool[n]) * gelu'(d_e)
+int launch_gate_bwd_apply(const __nv_bfloat16* gcs, const float* s, const float* gpool, const __nv_bfloat16* d_e, float* gi_f32,
+                          __nv_bfloat16* gz_de, int N, long hw, cudaStream_t st);
+
+// Weight repacking: fp32 [ntaps][R][Cc] (gradient layout) -> bf16, per-tap copy or transpose, taps gathered by tapmap.
+struct PackDesc {
+  long src_off;  // floats
+  long dst_off;  // bf16 elements
+  int ntaps, R, Cc, transpose;
+  signed char tapmap[16];
+};
+int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_dev, int ndesc, long max_elems, cudaStream_t st);
+
+}  // namespace refid

@@ -1,0 +1,1369 @@
+// The REFID network engine: a static launch plan for one (B,T,H,W) problem.
+//
+// `Engine::build_network` restates FinalBidirectionAttenfusion.forward (reference
+// basicsr/models/archs/XXNet_final_attenfusion_arch.py:130-218) as a sequence of tap-GEMM launches with fused
+// epilogues plus a handful of memory-bound kernels, recording a tape; replaying the tape in reverse emits the
+// backward plan (data-gradient tap-GEMMs with fused activation-derivative masks, weight-gradient GEMMs, reductions).
+// All tensor maps are encoded once at plan time; forward/backward are then pure launch loops on the caller's stream.
+//
+// Gradient convention: for an activation tensor X = act(Z) the gradient buffer holds dL/dZ ("GZ"): every consumer
+// multiplies its contribution by act'(.) (a linear mask) while accumulating, so the producer of X can feed the buffer
+// straight into its weight-gradient and data-gradient GEMMs.
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/refid_b200.h"
+#include "convop.cuh"
+#include "elementwise.cuh"
+
+namespace refid {
+
+namespace {
+
+enum SiteKind { SK_CONV3 = 0, SK_CONV1 = 1, SK_DOWN4 = 2, SK_UP2 = 3, SK_ROWS5 = 4, SK_RAW = 5 };
+
+struct Site {
+  std::string key;
+  int kind, taps, R, Cc, nbias;
+  long w_off, b_off;        // float offsets in the flat vector
+  long fwd_off, dgrad_off;  // bf16 element offsets in the pack region (-1: none)
+};
+
+struct Pend {
+  int g;     // gradient pool buffer (reference counted)
+  long off;  // byte offset of the addend in the workspace
+};
+
+struct Ten {
+  int N = 0, H = 0, W = 0, C = 0, pitch = 0;
+  long off = -1;  // byte offset in the workspace
+  int act = ACT_NONE;
+  float slope = 0.f;
+  long mask_off = -1;  // byte offset of the tensor act'(.) is evaluated on (own data, or the saved pre-activation)
+  bool need_grad = true;
+  bool f32acc = false;  // gradient accumulated in fp32 (many contributions over time), converted when finalized
+  long gfoff = -1;
+  bool gfwritten = false;
+  int gidx = -1;   // gradient pool buffer
+  long goff = -1;  // byte offset of the bf16 GZ buffer
+  bool gwritten = false;
+  int parent = -1;
+  long rel = 0;              // byte offset relative to the parent (views)
+  std::vector<Pend> pending;  // gradient buffers still to be added (residual / skip-sum passthrough)
+  bool contiguous() const { return pitch == C; }
+  long elems() const { return (long)N * H * W * C; }
+};
+
+struct GBuf {
+  size_t off, bytes;
+  int refs;
+};
+
+struct ConvOp {
+  int kind = CK_3X3;
+  int site = -1;
+  int in[2] = {-1, -1};
+  int nin = 1;
+  int out = -1;
+  int act = ACT_NONE;
+  float slope = 0.f;
+  int res = -1, res2 = -1;     // residual addends (added before the activation)
+  int post = -1, out2 = -1;    // out2 = out + post (skip sums)
+  bool nchw_out = false;       // pred: fp32 NCHW store into the caller's output tensor
+  long nchw_toff = 0, nchw_nstride = 0;
+  bool no_tape = false;
+};
+
+typedef std::function<int(cudaStream_t)> Launch;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct Engine {
+  refid_cfg cfg;
+  int Kp_img = 0, Kp_ev = 0;
+  std::vector<Site> sites;
+  std::map<std::string, int> site_idx;
+  long flat_floats = 0, pack_elems = 0, pack_max = 0;
+  std::vector<PackDesc> packs;
+  PackDesc* packs_dev = nullptr;
+
+  // plan state
+  bool planned = false, dry = false;
+  int B = 0, T = 0, H = 0, W = 0, train = 0;
+  char* ws = nullptr;
+  float* wmaster = nullptr;
+  __nv_bfloat16* wpackb = nullptr;
+  float* gflat = nullptr;
+  std::vector<Ten> tens;
+  std::map<std::string, int> named;
+  size_t act_top = 0, gbase = 0, gtop = 0;
+  std::vector<GBuf> gbufs;
+  std::multimap<size_t, int> gfree;
+  std::vector<Launch> fwd, bwd;
+  std::vector<Launch>* cur = nullptr;
+  std::vector<std::function<int()>> tape;
+  std::vector<std::pair<size_t, size_t>> f32_zero;
+  std::vector<int> release_after;  // pool buffers of pending addends consumed by the launch being built
+
+  // per-call io
+  const float* io_x = nullptr;
+  const float* io_ev = nullptr;
+  const float* io_gout = nullptr;
+  float* io_out = nullptr;
+
+  // ------------------------------------------------------------------------------------------
+  // parameter sites
+  // ------------------------------------------------------------------------------------------
+  int add_site(const std::string& key, int kind, int taps, int R, int Cc, int nbias, bool fwd_pack, bool dgrad_pack) {
+    Site s;
+    s.key = key;
+    s.kind = kind;
+    s.taps = taps;
+    s.R = R;
+    s.Cc = Cc;
+    s.nbias = nbias;
+    s.w_off = flat_floats;
+    flat_floats += (long)taps * R * Cc;
+    s.b_off = -1;
+    if (nbias > 0) {
+      s.b_off = flat_floats;
+      flat_floats += nbias;
+    }
+    flat_floats = (flat_floats + 3) / 4 * 4;  // keep every entry 16-byte aligned
+    s.fwd_off = s.dgrad_off = -1;
+    const long n = (long)taps * R * Cc;
+    auto add_pack = [&](int transpose, const int* tapmap) {
+      PackDesc d;
+      d.src_off = s.w_off;
+      d.dst_off = pack_elems;
+      d.ntaps = taps;
+      d.R = R;
+      d.Cc = Cc;
+      d.transpose = transpose;
+      for (int i = 0; i < 16; ++i) d.tapmap[i] = (signed char)(i < taps ? tapmap[i] : 0);
+      packs.push_back(d);
+      const long off = pack_elems;
+      pack_elems = (pack_elems + n + 63) / 64 * 64;  // 128-byte aligned matrices
+      if (n > pack_max) pack_max = n;
+      return off;
+    };
+    int ident[16], flip[16], down[16];
+    for (int i = 0; i < 16; ++i) {
+      ident[i] = i;
+      flip[i] = taps - 1 - i;
+    }
+    static const int kidx[2][2] = {{1, 3}, {0, 2}};  // [output parity][slot] -> kernel index (convop.cu: down_dgrad_off)
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) down[(py * 2 + px) * 4 + a * 2 + b] = kidx[py][a] * 4 + kidx[px][b];
+    switch (kind) {
+      case SK_CONV3:
+      case SK_CONV1:
+      case SK_ROWS5:
+        if (fwd_pack) s.fwd_off = add_pack(1, ident);
+        if (dgrad_pack) s.dgrad_off = add_pack(0, flip);
+        break;
+      case SK_DOWN4:
+        if (fwd_pack) s.fwd_off = add_pack(1, ident);
+        if (dgrad_pack) s.dgrad_off = add_pack(0, down);
+        break;
+      case SK_UP2:
+        if (fwd_pack) s.fwd_off = add_pack(0, ident);
+        if (dgrad_pack) s.dgrad_off = add_pack(1, ident);
+        break;
+      default:
+        break;
+    }
+    site_idx[key] = (int)sites.size();
+    sites.push_back(s);
+    return (int)sites.size() - 1;
+  }
+
+  int site(const std::string& key) {
+    auto it = site_idx.find(key);
+    if (it == site_idx.end()) {
+      set_error("unknown parameter site '%s'", key.c_str());
+      return -1;
+    }
+    return it->second;
+  }
+
+  void build_sites() {
+    const int b = cfg.base_num_channels;
+    Kp_img = (5 * cfg.img_chn + 31) / 32 * 32;
+    Kp_ev = (5 * cfg.ev_chn + 31) / 32 * 32;
+    auto trunk = [&](const std::string& p, int c) {
+      add_site(p + ".main.0", SK_CONV3, 9, 2 * c, c, c, true, true);
+      add_site(p + ".main.2.0.conv1", SK_CONV3, 9, c, c, c, true, true);
+      add_site(p + ".main.2.0.conv2", SK_CONV3, 9, c, c, c, true, true);
+    };
+    add_site("head_img", SK_ROWS5, 5, Kp_img, b, b, true, false);
+    add_site("head", SK_ROWS5, 5, Kp_ev, b, b, true, false);
+    for (int l = 0; l < 3; ++l) {
+      const int cin = b << l, c = b << (l + 1);
+      const std::string p = "img_encoders." + std::to_string(l);
+      add_site(p + ".conv_1", SK_CONV3, 9, cin, c, c, true, true);
+      add_site(p + ".conv_2", SK_CONV3, 9, c, c, c, true, true);
+      add_site(p + ".identity", SK_CONV1, 1, cin, c, c, true, true);
+      add_site(p + ".down", SK_DOWN4, 16, c, c, 0, true, true);
+    }
+    add_site("enc0_in", SK_CONV3, 9, b, 4 * b, 4 * b, true, true);  // both directions' level-0 in-convs, stacked on Cout
+    const char* dirs[2] = {"encoders_backward", "encoders_forward"};
+    for (int d = 0; d < 2; ++d)
+      for (int l = 0; l < 3; ++l) {
+        const int cin = b << l, c = b << (l + 1);
+        const std::string p = std::string(dirs[d]) + "." + std::to_string(l);
+        if (l == 2) add_site(p + ".conv", SK_CONV3, 9, cin, c, c, true, true);
+        if (l == 1) {
+          const std::string a = p + ".atten_fuse";
+          add_site(a + ".conv1", SK_CONV1, 1, cin, cin, cin, true, true);    // norm1 affine folded in
+          add_site(a + ".conv1_e", SK_CONV1, 1, cin, cin, cin, true, true);  // norm1_e affine folded in
+          add_site(a + ".conv2", SK_RAW, 1, cin, 9, cin, false, false);
+          add_site(a + ".conv2_e", SK_RAW, 1, cin, 9, cin, false, false);
+          add_site(a + ".se_1.1", SK_RAW, 1, cin / 2, cin, cin / 2, false, false);
+          add_site(a + ".se_1.3", SK_RAW, 1, cin, cin / 2, cin, false, false);
+          add_site(a + ".conv3", SK_CONV1, 1, 2 * cin, cin, cin, true, true);   // beta folded in
+          add_site(a + ".conv4", SK_CONV1, 1, cin, 2 * cin, 2 * cin, true, true);  // norm2 affine folded in
+          add_site(a + ".conv5s", SK_CONV1, 1, 3 * cin, c, c, true, true);  // [conv_y_side | gamma*conv5] on K = [y ; gelu]
+        }
+        trunk(p + ".recurrent_block.forward_trunk", c);
+        if (d == 1) add_site(p + ".fuse_two_dir", SK_CONV1, 1, 2 * c, c, c, true, true);
+        if (!(d == 0 && l == 2)) add_site(p + ".down", SK_DOWN4, 16, c, c, 0, true, true);
+      }
+    for (int i = 0; i < 2; ++i) {
+      const std::string p = "resblocks." + std::to_string(i);
+      add_site(p + ".conv1", SK_CONV3, 9, 8 * b, 8 * b, 8 * b, true, true);
+      add_site(p + ".conv2", SK_CONV3, 9, 8 * b, 8 * b, 8 * b, true, true);
+    }
+    for (int i = 0; i < 3; ++i) {
+      const int cin = (8 * b) >> i, c = cin / 2;
+      const std::string p = "decoders." + std::to_string(i);
+      add_site(p + ".transposed_conv2d", SK_UP2, 4, c, cin, c, true, true);
+      trunk(p + ".forward_trunk", c);
+    }
+    add_site("pred", SK_CONV3, 9, b, 32, 32, true, true);  // Cout padded out_chn -> 32
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // memory
+  // ------------------------------------------------------------------------------------------
+  __nv_bfloat16* P(long off) const { return reinterpret_cast<__nv_bfloat16*>(ws + off); }
+  float* PF(long off) const { return reinterpret_cast<float*>(ws + off); }
+
+  long act_alloc(size_t bytes) {
+    const size_t off = act_top;
+    act_top = align_up(act_top + bytes, 1024);
+    return (long)off;
+  }
+
+  int new_tensor(int N, int Hh, int Ww, int C, const std::string& name = "") {
+    Ten t;
+    t.N = N;
+    t.H = Hh;
+    t.W = Ww;
+    t.C = C;
+    t.pitch = C;
+    t.off = act_alloc((size_t)t.elems() * 2);
+    tens.push_back(t);
+    if (!name.empty()) named[name] = (int)tens.size() - 1;
+    return (int)tens.size() - 1;
+  }
+
+  int view(int parent, int n0, int N, int c0, int C) {
+    Ten t = tens[parent];
+    t.pending.clear();
+    t.rel = ((long)n0 * t.H * t.W * t.pitch + c0) * 2;
+    t.off += t.rel;
+    if (t.mask_off >= 0) t.mask_off += t.rel;
+    t.N = N;
+    t.C = C;
+    t.parent = parent;
+    t.gidx = -1;
+    t.goff = -1;
+    t.gwritten = false;
+    tens.push_back(t);
+    return (int)tens.size() - 1;
+  }
+
+  void mark_f32acc(int id) {
+    if (!train) return;
+    Ten& t = tens[id];
+    t.f32acc = true;
+    t.gfoff = act_alloc((size_t)t.elems() * 4);
+    f32_zero.push_back({(size_t)t.gfoff, (size_t)t.elems() * 4});
+  }
+
+  int galloc(size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    auto it = gfree.find(bytes);
+    if (it != gfree.end()) {
+      const int idx = it->second;
+      gfree.erase(it);
+      gbufs[idx].refs = 1;
+      return idx;
+    }
+    GBuf g;
+    g.off = gbase + gtop;
+    g.bytes = bytes;
+    g.refs = 1;
+    gtop += bytes;
+    gbufs.push_back(g);
+    return (int)gbufs.size() - 1;
+  }
+  void gunref(int idx) {
+    if (idx < 0) return;
+    if (--gbufs[idx].refs == 0) gfree.insert({gbufs[idx].bytes, idx});
+  }
+
+  void ensure_gbuf(int id) {
+    if (tens[id].goff >= 0) return;
+    if (tens[id].parent >= 0) {
+      const int p = tens[id].parent;
+      ensure_gbuf(p);
+      tens[p].gwritten = true;  // children fill the parent's buffer piecewise (each element exactly once)
+      tens[id].gidx = tens[p].gidx;
+      tens[id].goff = tens[p].goff + tens[id].rel;
+      return;
+    }
+    tens[id].gidx = galloc((size_t)tens[id].elems() * 2);
+    tens[id].goff = (long)gbufs[tens[id].gidx].off;
+  }
+
+  void emit(Launch l) {
+    if (!dry) cur->push_back(std::move(l));
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // gradient bookkeeping (plan time)
+  // ------------------------------------------------------------------------------------------
+  // Describes how a GEMM epilogue (or an elementwise kernel) adds its contribution into tensor `id`'s gradient.
+  struct Target {
+    __nv_bfloat16* dst = nullptr;
+    const __nv_bfloat16* pre = nullptr;   // existing contents (accumulate)
+    const __nv_bfloat16* pre2 = nullptr;  // one pending passthrough addend
+    const __nv_bfloat16* sv = nullptr;
+    int act = ACT_NONE;
+    float slope = 0.f;
+    float* dstf = nullptr;
+    int pitch = 0;
+  };
+
+  int flush_pending(int id, bool keep_one) {
+    // Fold pending passthrough addends into the gradient buffer with the masked-accumulate kernel.
+    while ((int)tens[id].pending.size() > (keep_one ? 1 : 0)) {
+      if (!tens[id].contiguous()) {
+        set_error("pending gradient on a strided view");
+        return 1;
+      }
+      ensure_gbuf(id);
+      AddMaskArgs a = {};
+      const int g0 = tens[id].pending.back().g;
+      a.a = P(tens[id].pending.back().off);
+      tens[id].pending.pop_back();
+      int g1 = -1;
+      if ((int)tens[id].pending.size() > (keep_one ? 1 : 0)) {
+        g1 = tens[id].pending.back().g;
+        a.b = P(tens[id].pending.back().off);
+        tens[id].pending.pop_back();
+      }
+      if (tens[id].act != ACT_NONE) {
+        a.sv = P(tens[id].mask_off);
+        a.act = tens[id].act;
+        a.slope = tens[id].slope;
+      }
+      a.dst = P(tens[id].goff);
+      a.dst_acc = tens[id].gwritten ? 1 : 0;
+      a.n = tens[id].elems();
+      tens[id].gwritten = true;
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); });
+      gunref(g0);
+      gunref(g1);
+    }
+    return 0;
+  }
+
+  int target(int id, Target* t) {
+    *t = Target();
+    t->pitch = tens[id].pitch;
+    if (tens[id].f32acc) {
+      t->dstf = PF(tens[id].gfoff);
+      tens[id].gfwritten = true;
+      return 0;
+    }
+    if (flush_pending(id, true)) return 1;
+    ensure_gbuf(id);
+    t->dst = P(tens[id].goff);
+    if (tens[id].gwritten) t->pre = t->dst;
+    if (!tens[id].pending.empty()) {
+      const int g = tens[id].pending.back().g;
+      t->pre2 = P(tens[id].pending.back().off);
+      tens[id].pending.pop_back();
+      release_after.push_back(g);
+    }
+    if (tens[id].act != ACT_NONE) {
+      t->sv = P(tens[id].mask_off);
+      t->act = tens[id].act;
+      t->slope = tens[id].slope;
+    }
+    tens[id].gwritten = true;
+    return 0;
+  }
+  void release_consumed() {
+    for (int g : release_after) gunref(g);
+    release_after.clear();
+  }
+
+  int add_pending(int id, int src_gidx, long src_off) {
+    if (id < 0 || !tens[id].need_grad) return 0;
+    if (tens[id].f32acc) {
+      AddMaskArgs a = {};
+      a.a = P(src_off);
+      a.dstf = PF(tens[id].gfoff);
+      a.n = tens[id].elems();
+      tens[id].gfwritten = true;
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); });
+      return 0;
+    }
+    gbufs[src_gidx].refs++;
+    tens[id].pending.push_back(Pend{src_gidx, src_off});
+    return 0;
+  }
+
+  // Complete tensor id's gradient; *gz = nullptr when no gradient reaches it.
+  int finalize(int id, const __nv_bfloat16** gz) {
+    *gz = nullptr;
+    if (!tens[id].need_grad) return 0;
+    if (tens[id].parent >= 0 && !tens[id].gwritten && tens[id].pending.empty()) {
+      const int p = tens[id].parent;
+      if (tens[p].gwritten || tens[p].goff >= 0) {
+        tens[id].gidx = tens[p].gidx;
+        tens[id].goff = tens[p].goff + tens[id].rel;
+        *gz = P(tens[id].goff);
+      }
+      return 0;
+    }
+    if (tens[id].f32acc) {
+      if (!tens[id].gfwritten) return 0;
+      ensure_gbuf(id);
+      AddMaskArgs a = {};
+      a.f = PF(tens[id].gfoff);
+      if (tens[id].act != ACT_NONE) {
+        a.sv = P(tens[id].mask_off);
+        a.act = tens[id].act;
+        a.slope = tens[id].slope;
+      }
+      a.dst = P(tens[id].goff);
+      a.n = tens[id].elems();
+      tens[id].gwritten = true;
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); });
+      *gz = P(tens[id].goff);
+      return 0;
+    }
+    if (flush_pending(id, false)) return 1;
+    if (!tens[id].gwritten) return 0;
+    *gz = P(tens[id].goff);
+    return 0;
+  }
+  void release_grad(int id) {
+    if (tens[id].parent >= 0) return;
+    if (tens[id].gidx >= 0) {
+      gunref(tens[id].gidx);
+      tens[id].gidx = -1;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // convolution ops
+  // ------------------------------------------------------------------------------------------
+  int conv(ConvOp op, const std::string& name = "") {
+    if (op.site < 0) return -1;
+    const Site& s = sites[op.site];
+    const Ten in0 = tens[op.in[0]];
+    const int cout = (op.kind == CK_UP2) ? s.R : s.Cc;
+    int oh = in0.H, ow = in0.W;
+    if (op.kind == CK_DOWN4) {
+      oh /= 2;
+      ow /= 2;
+    } else if (op.kind == CK_UP2) {
+      oh *= 2;
+      ow *= 2;
+    }
+    if (op.out < 0 && !op.nchw_out) {
+      op.out = new_tensor(in0.N, oh, ow, cout, name);
+      tens[op.out].act = op.act;
+      tens[op.out].slope = op.slope;
+      if (op.act == ACT_LRELU) tens[op.out].mask_off = tens[op.out].off;
+      if (op.act == ACT_GELU) tens[op.out].mask_off = act_alloc((size_t)tens[op.out].elems() * 2);
+    }
+    if (op.post >= 0 && op.out2 < 0) op.out2 = new_tensor(in0.N, oh, ow, cout, name.empty() ? "" : name + "+");
+    if (!dry) {
+      ConvDesc d;
+      memset(&d, 0, sizeof(d));
+      d.kind = op.kind;
+      d.nsrc = op.nin;
+      int cin_total = 0;
+      for (int k = 0; k < op.nin; ++k) {
+        const Ten& t = tens[op.in[k]];
+        d.src[k] = {P(t.off), t.C, t.pitch};
+        cin_total += t.C;
+      }
+      d.N = in0.N;
+      d.H = in0.H;
+      d.W = in0.W;
+      d.w = wpackb + s.fwd_off;
+      d.w_rows = (long)s.taps * cout;
+      d.w_cols = cin_total;
+      d.wrows_per_tap = cout;
+      d.w_row0 = 0;
+      const int expect_cin = (op.kind == CK_UP2) ? s.Cc : s.R;
+      if (cin_total != expect_cin) {
+        set_error("conv %s: input channels %d != %d", s.key.c_str(), cin_total, expect_cin);
+        return -1;
+      }
+      OutGroup g;
+      memset(&g, 0, sizeof(g));
+      g.channels = cout;
+      EpiDesc& e = g.epi;
+      if (op.nchw_out) {
+        e.C = cout;
+        e.nchw_C = cfg.out_chn;
+        e.nchw_nstride = op.nchw_nstride;
+      } else {
+        const Ten& o = tens[op.out];
+        e.out = P(o.off);
+        e.C = o.pitch;
+        if (op.act == ACT_GELU) e.out_pre = P(o.mask_off);
+      }
+      e.bias = s.b_off >= 0 ? wmaster + s.b_off : nullptr;
+      e.act = op.act;
+      e.slope = op.slope;
+      if (op.res >= 0) e.pre = P(tens[op.res].off);
+      if (op.res2 >= 0) e.pre2 = P(tens[op.res2].off);
+      if (op.out2 >= 0) {
+        e.out2 = P(tens[op.out2].off);
+        e.post = P(tens[op.post].off);
+      }
+      TapGemmLaunch l;
+      if (build_conv(d, &g, 1, &l)) return -1;
+      if (op.nchw_out) {
+        Engine* self = this;
+        const long toff = op.nchw_toff;
+        emit([l, self, toff](cudaStream_t st) mutable {
+          for (int i = 0; i < l.n_blocks; ++i) l.p.epi[i].out_nchw = self->io_out + toff;
+          return run_conv(l, st);
+        });
+      } else {
+        emit([l](cudaStream_t st) mutable { return run_conv(l, st); });
+      }
+    }
+    if (train && !op.no_tape) {
+      Engine* self = this;
+      tape.push_back([self, op]() { return self->conv_bwd(op); });
+    }
+    return op.out2 >= 0 && op.out < 0 ? op.out2 : op.out;
+  }
+
+  int emit_colsum(const __nv_bfloat16* gz, long rows, int C, float* dst) {
+    emit([gz, rows, C, dst](cudaStream_t s) { return launch_colsum(gz, rows, C, dst, s); });
+    return 0;
+  }
+
+  int conv_bwd(const ConvOp& op) {
+    const Site& s = sites[op.site];
+    if (op.out2 >= 0) {
+      const __nv_bfloat16* gs = nullptr;
+      if (finalize(op.out2, &gs)) return 1;
+      if (gs) {
+        const int g = tens[op.out2].gidx;
+        const long go = tens[op.out2].goff;
+        add_pending(op.out, g, go);
+        add_pending(op.post, g, go);
+      }
+      release_grad(op.out2);
+    }
+    const __nv_bfloat16* gz = nullptr;
+    if (finalize(op.out, &gz)) return 1;
+    if (!gz) return 0;
+    const Ten o = tens[op.out];
+    const Ten in0 = tens[op.in[0]];
+    const int cout = o.C;
+    int cin_total = 0;
+    for (int k = 0; k < op.nin; ++k) cin_total += tens[op.in[k]].C;
+    // bias gradient
+    if (s.b_off >= 0) {
+      REFID_REQUIRE(o.contiguous(), "bias gradient on a strided tensor (%s)", s.key.c_str());
+      emit_colsum(gz, (long)o.N * o.H * o.W, cout, gflat + s.b_off);
+    }
+    // weight gradient
+    if (!dry) {
+      ConvDesc d;
+      memset(&d, 0, sizeof(d));
+      ActSrc q;
+      if (op.kind == CK_UP2) {
+        d.kind = CK_UP2_DGRAD;
+        d.src[0] = {gz, o.C, o.pitch};
+        d.nsrc = 1;
+        d.N = o.N;
+        d.H = o.H;
+        d.W = o.W;
+        q = {P(in0.off), in0.C, in0.pitch};
+      } else {
+        d.kind = op.kind;
+        d.nsrc = op.nin;
+        for (int k = 0; k < op.nin; ++k) {
+          const Ten& t = tens[op.in[k]];
+          d.src[k] = {P(t.off), t.C, t.pitch};
+        }
+        d.N = in0.N;
+        d.H = in0.H;
+        d.W = in0.W;
+        q = {gz, o.C, o.pitch};
+      }
+      WgradLaunch wl;
+      if (build_wgrad(d, q, gflat + s.w_off, &wl)) return 1;
+      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); });
+    }
+    // data gradient
+    if (s.dgrad_off >= 0) {
+      int k = 0, chan0 = 0;
+      while (k < op.nin) {
+        if (!tens[op.in[k]].need_grad) {
+          chan0 += tens[op.in[k]].C;
+          ++k;
+          continue;
+        }
+        // maximal run of inputs that need a gradient -> one launch
+        OutGroup groups[2];
+        memset(groups, 0, sizeof(groups));
+        int ng = 0, w_row0 = chan0;
+        while (k < op.nin && tens[op.in[k]].need_grad) {
+          Target t;
+          if (target(op.in[k], &t)) return 1;
+          OutGroup& g = groups[ng++];
+          g.channels = tens[op.in[k]].C;
+          g.epi.out = t.dst;
+          g.epi.pre = t.pre;
+          g.epi.pre2 = t.pre2;
+          g.epi.sv = t.sv;
+          g.epi.act = t.act;
+          g.epi.slope = t.slope;
+          g.epi.out_f32 = t.dstf;
+          g.epi.C = t.pitch;
+          chan0 += tens[op.in[k]].C;
+          ++k;
+        }
+        if (!dry) {
+          const int launches = (op.kind == CK_DOWN4) ? 4 : 1;
+          for (int par = 0; par < launches; ++par) {
+            ConvDesc d;
+            memset(&d, 0, sizeof(d));
+            d.src[0] = {gz, o.C, o.pitch};
+            d.nsrc = 1;
+            d.N = o.N;
+            d.H = o.H;
+            d.W = o.W;
+            d.w = wpackb + s.dgrad_off;
+            d.w_cols = cout;
+            if (op.kind == CK_DOWN4) {
+              d.kind = CK_DOWN4_DGRAD;
+              d.parity = par;
+              d.w_rows = 16L * cin_total;
+              d.wrows_per_tap = cin_total;
+              d.w_row0 = par * 4 * cin_total + w_row0;
+            } else if (op.kind == CK_UP2) {
+              d.kind = CK_UP2_DGRAD;
+              d.w_rows = 4L * cin_total;
+              d.wrows_per_tap = cin_total;
+              d.w_row0 = w_row0;
+            } else {
+              d.kind = op.kind;
+              d.w_rows = (long)s.taps * cin_total;
+              d.wrows_per_tap = cin_total;
+              d.w_row0 = w_row0;
+            }
+            TapGemmLaunch l;
+            if (build_conv(d, groups, ng, &l)) return 1;
+            emit([l](cudaStream_t st) mutable { return run_conv(l, st); });
+          }
+        }
+        release_consumed();
+      }
+    }
+    if (op.res >= 0) add_pending(op.res, tens[op.out].gidx, tens[op.out].goff);
+    if (op.res2 >= 0) add_pending(op.res2, tens[op.out].gidx, tens[op.out].goff);
+    release_grad(op.out);
+    return 0;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // EGACA pieces (fusion_modules.py:290-333)
+  // ------------------------------------------------------------------------------------------
+  int ln(int x, const std::string& name = "") {
+    const Ten tx = tens[x];
+    const int y = new_tensor(tx.N, tx.H, tx.W, tx.C, name);
+    const long npix = (long)tx.N * tx.H * tx.W;
+    {
+      const __nv_bfloat16 *px = P(tx.off);
+      __nv_bfloat16* py = P(tens[y].off);
+      emit([px, py, npix](cudaStream_t s) { return launch_ln_fwd(px, py, npix, s); });
+    }
+    if (train) {
+      Engine* self = this;
+      tape.push_back([self, x, y, npix]() {
+        const __nv_bfloat16* gy = nullptr;
+        if (self->finalize(y, &gy)) return 1;
+        if (!gy || !self->tens[x].need_grad) return 0;
+        if (self->tens[x].act != ACT_NONE) {
+          set_error("LayerNorm input with an activation mask is unsupported");
+          return 1;
+        }
+        Target t;
+        if (self->target(x, &t)) return 1;
+        const __nv_bfloat16* px = self->P(self->tens[x].off);
+        self->emit([px, gy, t, npix](cudaStream_t s) {
+          return launch_ln_bwd(px, gy, t.pre2, t.dst, t.pre ? 1 : 0, t.dstf, npix, s);
+        });
+        self->release_consumed();
+        self->release_grad(y);
+        return 0;
+      });
+    }
+    return y;
+  }
+
+  // depthwise 3x3 + GELU (+ pooled sums); returns the GELU output tensor, *pre_out the saved pre-activation
+  int dw(int a, int site_id, long pool_off, const std::string& name = "") {
+    const Ten ta = tens[a];
+    const Site s = sites[site_id];
+    const int g = new_tensor(ta.N, ta.H, ta.W, ta.C, name);
+    tens[g].act = ACT_GELU;
+    tens[g].mask_off = act_alloc((size_t)ta.elems() * 2);
+    {
+      const __nv_bfloat16* pa = P(ta.off);
+      __nv_bfloat16 *pd = P(tens[g].mask_off), *pg = P(tens[g].off);
+      const float *w = wmaster + s.w_off, *b = wmaster + s.b_off;
+      float* pool = pool_off >= 0 ? PF(pool_off) : nullptr;
+      const int N = ta.N, Hh = ta.H, Ww = ta.W;
+      emit([pa, w, b, pd, pg, pool, N, Hh, Ww](cudaStream_t st) { return launch_dw_fwd(pa, w, b, pd, pg, pool, N, Hh, Ww, st); });
+    }
+    if (train) {
+      Engine* self = this;
+      tape.push_back([self, a, g, s]() {
+        const __nv_bfloat16* gz = nullptr;
+        if (self->finalize(g, &gz)) return 1;
+        if (!gz) return 0;
+        const Ten ta = self->tens[a];
+        self->ensure_gbuf(a);
+        self->tens[a].gwritten = true;
+        const __nv_bfloat16* pa = self->P(ta.off);
+        __nv_bfloat16* ga = self->P(self->tens[a].goff);
+        const float* w = self->wmaster + s.w_off;
+        float *gw = self->gflat + s.w_off, *gb = self->gflat + s.b_off;
+        const int N = ta.N, Hh = ta.H, Ww = ta.W;
+        self->emit([gz, pa, w, ga, gw, gb, N, Hh, Ww](cudaStream_t st) { return launch_dw_bwd(gz, pa, w, ga, gw, gb, N, Hh, Ww, st); });
+        self->release_grad(g);
+        return 0;
+      });
+    }
+    return g;
+  }
+
+  // One EGACA evaluation for direction `dir`: event feature xe (per step), image feature branch g_i (hoisted).
+  int egaca_step(int dir, int xe, int xi, int g_i, const std::string& nm) {
+    const std::string a = std::string(dir ? "encoders_forward" : "encoders_backward") + ".1.atten_fuse";
+    const Ten te = tens[xe];
+    const int N = te.N;
+    const long hw = (long)te.H * te.W;
+    const int n_e = ln(xe);
+    ConvOp c1;
+    c1.kind = CK_1X1;
+    c1.site = site(a + ".conv1_e");
+    c1.in[0] = n_e;
+    const int a_e = conv(c1);
+    if (a_e < 0) return -1;
+    // small fp32 state: pooled sums, gate, saved mean / hidden, and their gradients
+    const long small = act_alloc((size_t)N * (64 * 5 + 32) * 4);
+    const long pool_off = small, s_off = small + N * 64 * 4, mean_off = small + N * 128 * 4, gs_off = small + N * 192 * 4,
+               gpool_off = small + N * 256 * 4, z_off = small + N * 320 * 4;
+    {
+      char* p = ws + pool_off;
+      const size_t n = (size_t)N * 64 * 4;
+      emit([p, n](cudaStream_t st) {
+        REFID_CUDA_CHECK(cudaMemsetAsync(p, 0, n, st));
+        return 0;
+      });
+    }
+    const int g_e = dw(a_e, site(a + ".conv2_e"), pool_off, nm + ".g_e");
+    const int s1 = site(a + ".se_1.1"), s2 = site(a + ".se_1.3");
+    if (s1 < 0 || s2 < 0) return -1;
+    SeParams sp;
+    sp.w1 = wmaster + sites[s1].w_off;
+    sp.b1 = wmaster + sites[s1].b_off;
+    sp.w2 = wmaster + sites[s2].w_off;
+    sp.b2 = wmaster + sites[s2].b_off;
+    sp.gw1 = gflat ? gflat + sites[s1].w_off : nullptr;
+    sp.gb1 = gflat ? gflat + sites[s1].b_off : nullptr;
+    sp.gw2 = gflat ? gflat + sites[s2].w_off : nullptr;
+    sp.gb2 = gflat ? gflat + sites[s2].b_off : nullptr;
+    const float inv_hw = 1.f / (float)hw;
+    const int cs = new_tensor(N, te.H, te.W, 128, nm + ".cs");
+    {
+      float *pool = PF(pool_off), *sg = PF(s_off), *mean = PF(mean_off), *z = PF(z_off);
+      const __nv_bfloat16 *pgi = P(tens[g_i].off), *pge = P(tens[g_e].off);
+      __nv_bfloat16* pcs = P(tens[cs].off);
+      emit([pool, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, inv_hw, sp, sg, mean, z, N, st); });
+      emit([pgi, pge, sg, pcs, N, hw](cudaStream_t st) { return launch_gate_fwd(pgi, pge, sg, pcs, N, hw, st); });
+    }
+    if (train) {
+      Engine* self = this;
+      tape.push_back([self, cs, g_i, g_e, sp, inv_hw, N, hw, s_off, mean_off, z_off, gs_off, gpool_off]() {
+        const __nv_bfloat16* gcs = nullptr;
+        if (self->finalize(cs, &gcs)) return 1;
+        if (!gcs) return 0;
+        float *sg = self->PF(s_off), *mean = self->PF(mean_off), *z = self->PF(z_off), *gs = self->PF(gs_off),
+              *gpool = self->PF(gpool_off);
+        const __nv_bfloat16 *pgi = self->P(self->tens[g_i].off), *pge = self->P(self->tens[g_e].off);
+        const __nv_bfloat16* pde = self->P(self->tens[g_e].mask_off);
+        self->ensure_gbuf(g_e);
+        self->tens[g_e].gwritten = true;
+        __nv_bfloat16* gz_de = self->P(self->tens[g_e].goff);
+        float* gi_f32 = self->PF(self->tens[g_i].gfoff);
+        self->tens[g_i].gfwritten = true;
+        self->emit([gs, N](cudaStream_t st) {
+          REFID_CUDA_CHECK(cudaMemsetAsync(gs, 0, (size_t)N * 64 * 4, st));
+          return 0;
+        });
+        self->emit([gcs, pgi, pge, gs, N, hw](cudaStream_t st) { return launch_gate_bwd_reduce(gcs, pgi, pge, gs, N, hw, st); });
+        self->emit([gs, sg, mean, z, inv_hw, sp, gpool, N](cudaStream_t st) {
+          return launch_se_bwd(gs, sg, mean, z, inv_hw, sp, gpool, N, st);
+        });
+        self->emit([gcs, sg, gpool, pde, gi_f32, gz_de, N, hw](cudaStream_t st) {
+          return launch_gate_bwd_apply(gcs, sg, gpool, pde, gi_f32, gz_de, N, hw, st);
+        });
+        self->release_grad(cs);
+        return 0;
+      });
+    }
+    ConvOp c3;
+    c3.kind = CK_1X1;
+    c3.site = site(a + ".conv3");
+    c3.in[0] = cs;
+    c3.res = xe;
+    c3.res2 = xi;
+    const int y = conv(c3, nm + ".y");
+    if (y < 0) return -1;
+    const int n_y = ln(y);
+    ConvOp c4;
+    c4.kind = CK_1X1;
+    c4.site = site(a + ".conv4");
+    c4.in[0] = n_y;
+    c4.act = ACT_GELU;
+    const int g4 = conv(c4);
+    if (g4 < 0) return -1;
+    ConvOp c5;
+    c5.kind = CK_1X1;
+    c5.site = site(a + ".conv5s");
+    c5.in[0] = y;
+    c5.in[1] = g4;
+    c5.nin = 2;
+    return conv(c5, nm + ".u");
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // the network
+  // ------------------------------------------------------------------------------------------
+  int zero_tensor(int N, int Hh, int Ww, int C, std::vector<std::pair<size_t, size_t>>* zero_list) {
+    const int id = new_tensor(N, Hh, Ww, C);
+    tens[id].need_grad = false;
+    zero_list->push_back({(size_t)tens[id].off, (size_t)tens[id].elems() * 2});
+    return id;
+  }
+
+  int trunk(const std::string& p, int u, int hprev, const std::string& nm, int post, int out2_preset, int* out2) {
+    ConvOp a;
+    a.site = site(p + ".main.0");
+    a.in[0] = u;
+    a.in[1] = hprev;
+    a.nin = 2;
+    a.act = ACT_LRELU;
+    a.slope = 0.1f;
+    const int v = conv(a, nm + ".v");
+    if (v < 0) return -1;
+    ConvOp b;
+    b.site = site(p + ".main.2.0.conv1");
+    b.in[0] = v;
+    b.act = ACT_LRELU;
+    b.slope = 0.f;
+    const int r = conv(b);
+    if (r < 0) return -1;
+    ConvOp c;
+    c.site = site(p + ".main.2.0.conv2");
+    c.in[0] = r;
+    c.res = v;
+    c.post = post;
+    c.out2 = out2_preset;
+    const int h = conv(c, nm + ".h");
+    if (h < 0) return -1;
+    if (out2) *out2 = post >= 0 ? (out2_preset >= 0 ? out2_preset : (int)tens.size() - 1) : -1;
+    return h;
+  }
+
+  int build_network() {
+    const int b = cfg.base_num_channels;
+    std::vector<std::pair<size_t, size_t>> zero_fwd;
+    Engine* self = this;
+    // ---- image branch: head_img, three ImageEncoderConvBlocks (recurrent_sub_modules.py:22-49)
+    const int ximg = new_tensor(B, H, W, Kp_img);
+    tens[ximg].need_grad = false;
+    {
+      __nv_bfloat16* o = P(tens[ximg].off);
+      const int Bc = B, Cin = cfg.img_chn, Hh = H, Ww = W, Kp = Kp_img;
+      emit([self, o, Bc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_x, o, Bc, 1, Cin, Hh, Ww, Kp, st); });
+    }
+    ConvOp hi;
+    hi.kind = CK_ROWS5;
+    hi.site = site("head_img");
+    hi.in[0] = ximg;
+    hi.act = ACT_LRELU;
+    hi.slope = 0.2f;
+    const int head = conv(hi, "head_img");
+    if (head < 0) return 1;
+    mark_f32acc(head);
+    int xb[3];
+    int f = head;
+    for (int l = 0; l < 3; ++l) {
+      const std::string p = "img_encoders." + std::to_string(l);
+      ConvOp c1;
+      c1.site = site(p + ".conv_1");
+      c1.in[0] = f;
+      c1.act = ACT_LRELU;
+      c1.slope = 0.2f;
+      const int t1 = conv(c1);
+      ConvOp ci;
+      ci.kind = CK_1X1;
+      ci.site = site(p + ".identity");
+      ci.in[0] = f;
+      const int idn = conv(ci);
+      if (t1 < 0 || idn < 0) return 1;
+      ConvOp c2;
+      c2.site = site(p + ".conv_2");
+      c2.in[0] = t1;
+      c2.act = ACT_LRELU;
+      c2.slope = 0.2f;
+      c2.post = idn;
+      if (conv(c2) < 0) return 1;
+      const int sum = (int)tens.size() - 1;
+      ConvOp cd;
+      cd.kind = CK_DOWN4;
+      cd.site = site(p + ".down");
+      cd.in[0] = sum;
+      xb[l] = conv(cd, "xb" + std::to_string(l));
+      if (xb[l] < 0) return 1;
+      mark_f32acc(xb[l]);
+      f = xb[l];
+    }
+    // ---- event head over all T slices at once, then both directions' level-0 in-convs (recurrence independent)
+    const int xev = new_tensor(T * B, H, W, Kp_ev);
+    tens[xev].need_grad = false;
+    {
+      __nv_bfloat16* o = P(tens[xev].off);
+      const int Bc = B, Tc = T, Cin = cfg.ev_chn, Hh = H, Ww = W, Kp = Kp_ev;
+      emit([self, o, Bc, Tc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_ev, o, Bc, Tc, Cin, Hh, Ww, Kp, st); });
+    }
+    ConvOp he;
+    he.kind = CK_ROWS5;
+    he.site = site("head");
+    he.in[0] = xev;
+    he.act = ACT_LRELU;
+    he.slope = 0.2f;
+    const int e_all = conv(he, "e_all");
+    if (e_all < 0) return 1;
+    ConvOp cu;
+    cu.site = site("enc0_in");
+    cu.in[0] = e_all;
+    cu.act = ACT_LRELU;
+    cu.slope = 0.04f;  // ConvLayer's LeakyReLU(0.2) applied twice (recurrent_sub_modules.py:283-285)
+    const int u0_all = conv(cu, "u0_all");
+    if (u0_all < 0) return 1;
+    // ---- EGACA image branch, once per direction (image feature is constant over time)
+    int g_i[2];
+    for (int d = 0; d < 2; ++d) {
+      const std::string a = std::string(d ? "encoders_forward" : "encoders_backward") + ".1.atten_fuse";
+      const int n_i = ln(xb[0]);
+      ConvOp c1;
+      c1.kind = CK_1X1;
+      c1.site = site(a + ".conv1");
+      c1.in[0] = n_i;
+      const int a_i = conv(c1);
+      if (a_i < 0) return 1;
+      g_i[d] = dw(a_i, site(a + ".conv2"), -1, d ? "f.g_i" : "b.g_i");
+      mark_f32acc(g_i[d]);
+    }
+    const char* dirs[2] = {"encoders_backward", "encoders_forward"};
+    // ---- backward sweep t = T-1 .. 0 (XXNet_final_attenfusion_arch.py:172-181)
+    int hb[3];
+    for (int l = 0; l < 3; ++l) hb[l] = zero_tensor(B, H >> l, W >> l, (2 * b) << l, &zero_fwd);
+    for (int t = T - 1; t >= 0; --t) {
+      int curx = -1;
+      for (int l = 0; l < 3; ++l) {
+        const std::string p = std::string(dirs[0]) + "." + std::to_string(l);
+        const std::string nm = "b.t" + std::to_string(t) + ".l" + std::to_string(l);
+        int u;
+        if (l == 0) {
+          u = view(u0_all, t * B, B, 0, 2 * b);
+        } else if (l == 1) {
+          u = egaca_step(0, curx, xb[0], g_i[0], nm);
+        } else {
+          ConvOp ci;
+          ci.site = site(p + ".conv");
+          ci.in[0] = curx;
+          ci.act = ACT_LRELU;
+          ci.slope = 0.04f;
+          u = conv(ci, nm + ".u");
+        }
+        if (u < 0) return 1;
+        const int h = trunk(p + ".recurrent_block.forward_trunk", u, hb[l], nm, -1, -1, nullptr);
+        if (h < 0) return 1;
+        hb[l] = h;
+        if (l < 2) {
+          ConvOp cd;
+          cd.kind = CK_DOWN4;
+          cd.site = site(p + ".down");
+          cd.in[0] = h;
+          if (l == 1) cd.post = xb[1];
+          const int dn = conv(cd, nm + ".d");
+          if (dn < 0) return 1;
+          curx = (l == 1) ? (int)tens.size() - 1 : dn;
+        }
+      }
+    }
+    // Only the FINAL backward state reaches the forward sweep (list aliasing at :181).
+    for (int l = 0; l < 3; ++l) mark_f32acc(hb[l]);
+    // ---- forward sweep t = 0 .. T-1 (:185-216)
+    int hf[3], sd[3];
+    for (int l = 0; l < 3; ++l) hf[l] = zero_tensor(B, H >> l, W >> l, (2 * b) << l, &zero_fwd);
+    for (int i = 0; i < 3; ++i) sd[i] = zero_tensor(B, H >> (2 - i), W >> (2 - i), (4 * b) >> i, &zero_fwd);
+    const int sp_all = new_tensor(T * B, H, W, b, "sp_all");
+    for (int t = 0; t < T; ++t) {
+      int curx = -1;
+      int dn[3];
+      for (int l = 0; l < 3; ++l) {
+        const std::string p = std::string(dirs[1]) + "." + std::to_string(l);
+        const std::string nm = "f.t" + std::to_string(t) + ".l" + std::to_string(l);
+        int u;
+        if (l == 0) {
+          u = view(u0_all, t * B, B, 2 * b, 2 * b);
+        } else if (l == 1) {
+          u = egaca_step(1, curx, xb[0], g_i[1], nm);
+        } else {
+          ConvOp ci;
+          ci.site = site(p + ".conv");
+          ci.in[0] = curx;
+          ci.act = ACT_LRELU;
+          ci.slope = 0.04f;
+          u = conv(ci, nm + ".u");
+        }
+        if (u < 0) return 1;
+        const int h = trunk(p + ".recurrent_block.forward_trunk", u, hf[l], nm, -1, -1, nullptr);
+        if (h < 0) return 1;
+        hf[l] = h;
+        ConvOp cf;
+        cf.kind = CK_1X1;
+        cf.site = site(p + ".fuse_two_dir");
+        cf.in[0] = h;
+        cf.in[1] = hb[l];
+        cf.nin = 2;
+        cf.act = ACT_LRELU;
+        cf.slope = 0.2f;
+        const int hfu = conv(cf);
+        if (hfu < 0) return 1;
+        ConvOp cd;
+        cd.kind = CK_DOWN4;
+        cd.site = site(p + ".down");
+        cd.in[0] = hfu;
+        if (l >= 1) cd.post = xb[l];
+        dn[l] = conv(cd, nm + ".d");
+        if (dn[l] < 0) return 1;
+        curx = (l >= 1) ? (int)tens.size() - 1 : dn[l];
+      }
+      // bottleneck: two ResidualBlocks (recurrent_sub_modules.py:468-503)
+      int xin = curx;
+      for (int i = 0; i < 2; ++i) {
+        const std::string p = "resblocks." + std::to_string(i);
+        ConvOp c1;
+        c1.site = site(p + ".conv1");
+        c1.in[0] = xin;
+        c1.act = ACT_LRELU;
+        c1.slope = 0.f;
+        const int r = conv(c1);
+        if (r < 0) return 1;
+        ConvOp c2;
+        c2.site = site(p + ".conv2");
+        c2.in[0] = r;
+        c2.res = xin;
+        c2.act = ACT_LRELU;
+        c2.slope = 0.f;
+        if (i == 1) c2.post = dn[2];
+        const int o = conv(c2, "f.t" + std::to_string(t) + ".res" + std::to_string(i));
+        if (o < 0) return 1;
+        xin = (i == 1) ? (int)tens.size() - 1 : o;
+      }
+      // decoders (TransposeRecurrentConvLayer, :370-408); input = previous + encoder skip (skip_sum, :211)
+      for (int i = 0; i < 3; ++i) {
+        const std::string p = "decoders." + std::to_string(i);
+        const std::string nm = "f.t" + std::to_string(t) + ".dec" + std::to_string(i);
+        ConvOp up;
+        up.kind = CK_UP2;
+        up.site = site(p + ".transposed_conv2d");
+        up.in[0] = xin;
+        const int u = conv(up, nm + ".up");
+        if (u < 0) return 1;
+        int post, preset = -1, o2 = -1;
+        if (i < 2) {
+          post = dn[1 - i];
+        } else {
+          post = head;
+          preset = view(sp_all, t * B, B, 0, b);
+        }
+        const int s = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2);
+        if (s < 0) return 1;
+        sd[i] = s;
+        xin = o2;
+      }
+      // prediction for this step straight into the caller's (B,T,out_chn,H,W) tensor
+      ConvOp cp;
+      cp.site = site("pred");
+      cp.in[0] = xin;
+      cp.nchw_out = true;
+      cp.no_tape = true;
+      cp.nchw_toff = (long)t * cfg.out_chn * H * W;
+      cp.nchw_nstride = (long)T * cfg.out_chn * H * W;
+      conv(cp);
+    }
+    // pred backward is batched over all T steps: gout -> bf16 NHWC (padded to 32 channels), wgrad + dgrad once
+    if (train) {
+      const int ps = site("pred");
+      tape.push_back([self, sp_all, ps]() {
+        Ten t;
+        t.N = self->T * self->B;
+        t.H = self->H;
+        t.W = self->W;
+        t.C = t.pitch = 32;
+        t.off = 0;
+        self->tens.push_back(t);
+        const int pg = (int)self->tens.size() - 1;
+        self->ensure_gbuf(pg);
+        self->tens[pg].gwritten = true;
+        __nv_bfloat16* dst = self->P(self->tens[pg].goff);
+        const int Bc = self->B, Tc = self->T, Cv = self->cfg.out_chn, Hh = self->H, Ww = self->W;
+        self->emit([self, dst, Bc, Tc, Cv, Hh, Ww](cudaStream_t st) {
+          return launch_gout_pack(self->io_gout, dst, Bc, Tc, Cv, Hh, Ww, st);
+        });
+        ConvOp op;
+        op.site = ps;
+        op.in[0] = sp_all;
+        op.out = pg;
+        return self->conv_bwd(op);
+      });
+    }
+    // workspace zeroing for the t = 0 recurrent states goes first in the forward list
+    if (!dry) {
+      std::vector<Launch> pre;
+      for (auto& z : zero_fwd) {
+        char* p = ws + z.first;
+        const size_t n = z.second;
+        pre.push_back([p, n](cudaStream_t st) {
+          REFID_CUDA_CHECK(cudaMemsetAsync(p, 0, n, st));
+          return 0;
+        });
+      }
+      fwd.insert(fwd.begin(), pre.begin(), pre.end());
+    }
+    return 0;
+  }
+
+  int plan(int B_, int T_, int H_, int W_, int train_, void* workspace, void* wpack, float* grad_flat, bool dry_) {
+    REFID_REQUIRE(B_ >= 1 && T_ >= 1 && H_ >= 8 && W_ >= 8 && H_ % 8 == 0 && W_ % 8 == 0,
+                  "plan: need B,T >= 1 and H,W multiples of 8 (got B%d T%d H%d W%d)", B_, T_, H_, W_);
+    B = B_;
+    T = T_;
+    H = H_;
+    W = W_;
+    train = train_;
+    dry = dry_;
+    ws = static_cast<char*>(workspace);
+    wmaster = static_cast<float*>(wpack);
+    wpackb = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(wpack) + align_up((size_t)flat_floats * 4, 1024));
+    gflat = grad_flat;
+    REFID_REQUIRE(dry || !train || gflat, "plan: grad_flat is required when train != 0");
+    tens.clear();
+    named.clear();
+    gbufs.clear();
+    gfree.clear();
+    fwd.clear();
+    bwd.clear();
+    tape.clear();
+    f32_zero.clear();
+    release_after.clear();
+    act_top = gtop = 0;
+    planned = false;
+    cur = &fwd;
+    if (build_network()) return 1;
+    gbase = act_top;
+    cur = &bwd;
+    if (train) {
+      for (auto& z : f32_zero) {
+        char* p = ws + z.first;
+        const size_t n = z.second;
+        emit([p, n](cudaStream_t st) {
+          REFID_CUDA_CHECK(cudaMemsetAsync(p, 0, n, st));
+          return 0;
+        });
+      }
+      for (int i = (int)tape.size() - 1; i >= 0; --i)
+        if (tape[i]()) return 1;
+    }
+    tape.clear();
+    planned = !dry;
+    return 0;
+  }
+};
+
+}  // namespace refid
+
+using refid::Engine;
+
+extern "C" {
+
+int refid_create(const refid_cfg* cfg, refid_handle* out) {
+  using namespace refid;
+  REFID_REQUIRE(cfg && out, "refid_create: null argument");
+  REFID_REQUIRE(cfg->base_num_channels == 32, "refid_create: base_num_channels must be 32 (got %d)", cfg->base_num_channels);
+  REFID_REQUIRE(cfg->img_chn >= 1 && cfg->img_chn <= 64 && cfg->ev_chn >= 1 && cfg->ev_chn <= 64,
+                "refid_create: img_chn/ev_chn out of range");
+  REFID_REQUIRE(cfg->out_chn >= 1 && cfg->out_chn <= 8, "refid_create: out_chn must be 1..8");
+  Engine* e = new Engine();
+  e->cfg = *cfg;
+  e->build_sites();
+  *out = reinterpret_cast<refid_handle>(e);
+  return 0;
+}
+
+int refid_destroy(refid_handle h) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e) return 0;
+  if (e->packs_dev) cudaFree(e->packs_dev);
+  delete e;
+  return 0;
+}
+
+int refid_num_param_entries(refid_handle h) { return (int)reinterpret_cast<Engine*>(h)->sites.size(); }
+
+int refid_param_entry_at(refid_handle h, int idx, refid_param_entry* out) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(idx >= 0 && idx < (int)e->sites.size(), "param entry %d out of range", idx);
+  const auto& s = e->sites[idx];
+  memset(out, 0, sizeof(*out));
+  snprintf(out->key, sizeof(out->key), "%s", s.key.c_str());
+  out->kind = s.kind;
+  out->taps = s.taps;
+  out->R = s.R;
+  out->Cc = s.Cc;
+  out->nbias = s.nbias;
+  out->w_off = s.w_off;
+  out->b_off = s.b_off;
+  return 0;
+}
+
+long refid_flat_floats(refid_handle h) { return reinterpret_cast<Engine*>(h)->flat_floats; }
+
+size_t refid_wpack_bytes(refid_handle h) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  return refid::align_up((size_t)e->flat_floats * 4, 1024) + (size_t)e->pack_elems * 2 + 1024;
+}
+
+int refid_workspace_bytes(refid_handle h, int B, int T, int H, int W, int train, size_t* out) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (e->plan(B, T, H, W, train, nullptr, nullptr, nullptr, true)) return 1;
+  *out = e->gbase + e->gtop + 4096;
+  return 0;
+}
+
+int refid_plan(refid_handle h, int B, int T, int H, int W, int train, void* workspace, void* wpack, float* grad_flat) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(workspace && wpack, "refid_plan: null buffer");
+  REFID_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 255) == 0,
+                "refid_plan: workspace and wpack must be 256-byte aligned");
+  return e->plan(B, T, H, W, train, workspace, wpack, grad_flat, false);
+}
+
+int refid_pack_weights(refid_handle h, const float* flat, void* stream) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(e->planned, "refid_pack_weights: call refid_plan first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!e->packs_dev) {
+    REFID_CUDA_CHECK(cudaMalloc(&e->packs_dev, e->packs.size() * sizeof(PackDesc)));  // 10s of KB of descriptors, not data
+    REFID_CUDA_CHECK(cudaMemcpy(e->packs_dev, e->packs.data(), e->packs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
+  }
+  REFID_CUDA_CHECK(cudaMemcpyAsync(e->wmaster, flat, (size_t)e->flat_floats * 4, cudaMemcpyDeviceToDevice, st));
+  return launch_pack(flat, e->wpackb, e->packs_dev, (int)e->packs.size(), e->pack_max, st);
+}
+
+int refid_forward(refid_handle h, const float* x, const float* event, float* out, void* stream) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(e->planned, "refid_forward: no plan");
+  REFID_REQUIRE(x && event && out, "refid_forward: null tensor");
+  e->io_x = x;
+  e->io_ev = event;
+  e->io_out = out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& l : e->fwd)
+    if (l(st)) return 1;
+  return 0;
+}
+
+int refid_backward(refid_handle h, const float* grad_out, void* stream) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(e->planned && e->train, "refid_backward: no training plan");
+  REFID_REQUIRE(grad_out, "refid_backward: null tensor");
+  e->io_gout = grad_out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  REFID_CUDA_CHECK(cudaMemsetAsync(e->gflat, 0, (size_t)e->flat_floats * 4, st));
+  for (auto& l : e->bwd)
+    if (l(st)) return 1;
+  return 0;
+}
+
+int refid_num_launches(refid_handle h, int* fwd, int* bwd) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (fwd) *fwd = (int)e->fwd.size();
+  if (bwd) *bwd = (int)e->bwd.size();
+  return 0;
+}
+
+int refid_debug_tensor(refid_handle h, const char* name, void** ptr, int* N, int* H, int* W, int* C, int* pitch) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  auto it = e->named.find(name);
+  REFID_REQUIRE(it != e->named.end(), "no tensor named '%s'", name);
+  const auto& t = e->tens[it->second];
+  *ptr = e->ws + t.off;
+  *N = t.N;
+  *H = t.H;
+  *W = t.W;
+  *C = t.C;
+  *pitch = t.pitch;
+  return 0;
+}
+
+}  // extern "C"

@@ -4,4 +4,6 @@
 #include "tapgemm.cu"
 #include "wgrad.cu"
 #include "convop.cu"
+#include "elementwise.cu"
+#include "engine.cu"
 #include "api_test.cu"

@@ -7,11 +7,6 @@ namespace {
 
 constexpr int kThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
-
 __device__ __forceinline__ void load16(const __nv_bfloat16* p, float* f) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = q[0], b = q[1];
@@ -186,6 +181,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
           }
         }
         if (e.out) store16(e.out + base + c0, v);
+        if (e.out_nchw && c0 == 0) {
+          float* o = e.out_nchw + (size_t)n * e.nchw_nstride + (size_t)(y * e.osy + e.ooy) * e.OW + (size_t)(x * e.osx + e.oox);
+          const size_t plane = (size_t)e.OH * e.OW;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < e.nchw_C) o[i * plane] = v[i];
+        }
         if (e.out_f32) {
           float4* o = reinterpret_cast<float4*>(e.out_f32 + base + c0);
 #pragma unroll

@@ -21,12 +21,15 @@ enum ActKind : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2 };
 //   a = acc + bias[n*bias_nstride + c] + pre + pre2
 //   if sv:  a *= act'(sv)      (LRELU: sv>0 ? 1 : slope, evaluated on the saved OUTPUT; GELU: on the saved PRE-activation)
 //   else :  if out_pre: out_pre = a;   a = act(a)
-//   out = a;  out_f32 += a;  out2 = a + post
+//   out = a;  out_f32 += a;  out2 = a + post;  out_nchw[c < nchw_C] = a
 struct EpiDesc {
   __nv_bfloat16* out;
   __nv_bfloat16* out2;
   __nv_bfloat16* out_pre;
   float* out_f32;
+  float* out_nchw;      // optional fp32 NCHW store of the first nchw_C channels (pred): [n*nchw_nstride + c*OH*OW + y*OW + x]
+  long nchw_nstride;
+  int nchw_C;
   const __nv_bfloat16* post;
   const __nv_bfloat16* pre;
   const __nv_bfloat16* pre2;
