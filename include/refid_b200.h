@@ -73,6 +73,11 @@ int refid_forward(refid_handle h, const float* x, const float* event, float* out
  * Must follow a refid_forward on the same plan (train != 0). */
 int refid_backward(refid_handle h, const float* grad_out, void* stream);
 
+/* Roofline accounting: re-runs forward (+ backward) of the current plan on the tensors of the last call with a CUDA
+ * event pair around every launch; sums device milliseconds, algorithmic FLOPs and launch counts per class:
+ * [0] conv forward tap-GEMM, [1] data-gradient tap-GEMM, [2] weight-gradient GEMM, [3] memory-bound kernels. */
+int refid_profile(refid_handle h, int with_backward, double ms[4], double flops[4], long launches[4], void* stream);
+
 /* Introspection used by tests and profiling. */
 int refid_num_launches(refid_handle h, int* fwd, int* bwd);
 /* Device pointer + shape of a named intermediate activation (NHWC bf16, `pitch` channels per pixel). */

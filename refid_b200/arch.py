@@ -93,14 +93,14 @@ class _RefidFunction(torch.autograd.Function):
     def forward(ctx, x, event, flat, mod):
         B, T = event.shape[:2]
         H, W = event.shape[-2:]
-        train = bool(flat.requires_grad) and torch.is_grad_enabled()
+        train = bool(ctx.needs_input_grad[2])
         st = mod._state_for(B, T, H, W, train, x.device)
         eng = st["engine"]
         eng.pack_weights(flat.detach().contiguous())
         out = torch.empty(B, T, mod.out_chn, H, W, device=x.device, dtype=torch.float32)
         eng.forward(x, event, out)
         st["generation"] += 1
-        ctx.st, ctx.generation = st, st["generation"]
+        ctx.st, ctx.generation, ctx.mod = st, st["generation"], mod
         return out
 
     @staticmethod
@@ -110,7 +110,14 @@ class _RefidFunction(torch.autograd.Function):
             raise RuntimeError("refid_b200: the activations saved for this backward were overwritten by a later forward "
                                "of the same shape (one forward/backward in flight per module and shape)")
         st["engine"].backward(grad_out.contiguous().float())
-        return None, None, st["grad_flat"].clone(), None
+        g = st["grad_flat"]
+        group = getattr(ctx.mod, "grad_sync_group", None)
+        if group is not None:
+            # Data parallelism: the only collective on the path is this all-reduce (mean) of the flat gradient --
+            # one contiguous NCCL call over NVLink/NVSwitch instead of DDP's per-bucket reduction.
+            import torch.distributed as dist
+            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=group)
+        return None, None, g.clone(), None
 
 
 class FinalBidirectionAttenfusion(nn.Module):
@@ -165,6 +172,7 @@ class FinalBidirectionAttenfusion(nn.Module):
             d.forward_trunk = _trunk(cin, cin // 2)
             self.decoders.append(d)
         self.pred = _conv_layer(b, out_chn, 3, 1)
+        self.grad_sync_group = None  # set to a torch.distributed group for the flat-gradient all-reduce (no DDP wrapper)
         self._engines = {}   # device -> Engine (parameter table)
         self._states = {}    # (B,T,H,W,train,device) -> planned engine + buffers
 

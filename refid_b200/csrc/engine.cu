@@ -78,6 +78,13 @@ struct ConvOp {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
+// launch classes for the roofline accounting (bench.py)
+enum LaunchClass { LC_CONV_FWD = 0, LC_CONV_DGRAD = 1, LC_WGRAD = 2, LC_OTHER = 3, LC_COUNT = 4 };
+struct LaunchMeta {
+  int cls;
+  double flops;  // algorithmic FLOPs (2*MAC on un-padded channel counts); 0 for memory-bound kernels
+};
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -104,6 +111,7 @@ struct Engine {
   std::vector<GBuf> gbufs;
   std::multimap<size_t, int> gfree;
   std::vector<Launch> fwd, bwd;
+  std::vector<LaunchMeta> fwd_meta, bwd_meta;
   std::vector<Launch>* cur = nullptr;
   std::vector<std::function<int()>> tape;
   std::vector<std::pair<size_t, size_t>> f32_zero;
@@ -334,8 +342,22 @@ struct Engine {
     tens[id].goff = (long)gbufs[tens[id].gidx].off;
   }
 
-  void emit(Launch l) {
-    if (!dry) cur->push_back(std::move(l));
+  void emit(Launch l, int cls = LC_OTHER, double flops = 0.0) {
+    if (dry) return;
+    cur->push_back(std::move(l));
+    (cur == &fwd ? fwd_meta : bwd_meta).push_back(LaunchMeta{cls, flops});
+  }
+
+  // algorithmic FLOPs of one convolution (forward = data-gradient = weight-gradient)
+  double conv_flops(const ConvOp& op) const {
+    const Site& s = sites[op.site];
+    const Ten& in0 = tens[op.in[0]];
+    const double pix = (double)in0.N * in0.H * in0.W;
+    if (op.kind == CK_ROWS5) return 2.0 * pix * 25.0 * (s.key == "head" ? cfg.ev_chn : cfg.img_chn) * s.Cc;
+    if (op.kind == CK_UP2) return 2.0 * pix * 4.0 * s.Cc * s.R;
+    if (op.kind == CK_DOWN4) return 2.0 * (pix / 4.0) * 16.0 * s.R * s.Cc;
+    const double cout = (s.key == "pred") ? cfg.out_chn : s.Cc;
+    return 2.0 * pix * s.taps * s.R * cout;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -556,9 +578,9 @@ struct Engine {
         emit([l, self, toff](cudaStream_t st) mutable {
           for (int i = 0; i < l.n_blocks; ++i) l.p.epi[i].out_nchw = self->io_out + toff;
           return run_conv(l, st);
-        });
+        }, LC_CONV_FWD, conv_flops(op));
       } else {
-        emit([l](cudaStream_t st) mutable { return run_conv(l, st); });
+        emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, LC_CONV_FWD, conv_flops(op));
       }
     }
     if (train && !op.no_tape) {
@@ -626,7 +648,7 @@ struct Engine {
       }
       WgradLaunch wl;
       if (build_wgrad(d, q, gflat + s.w_off, &wl)) return 1;
-      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); });
+      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, conv_flops(op));
     }
     // data gradient
     if (s.dgrad_off >= 0) {
@@ -640,12 +662,13 @@ struct Engine {
         // maximal run of inputs that need a gradient -> one launch
         OutGroup groups[2];
         memset(groups, 0, sizeof(groups));
-        int ng = 0, w_row0 = chan0;
+        int ng = 0, w_row0 = chan0, grad_ch = 0;
         while (k < op.nin && tens[op.in[k]].need_grad) {
           Target t;
           if (target(op.in[k], &t)) return 1;
           OutGroup& g = groups[ng++];
           g.channels = tens[op.in[k]].C;
+          grad_ch += g.channels;
           g.epi.out = t.dst;
           g.epi.pre = t.pre;
           g.epi.pre2 = t.pre2;
@@ -688,7 +711,8 @@ struct Engine {
             }
             TapGemmLaunch l;
             if (build_conv(d, groups, ng, &l)) return 1;
-            emit([l](cudaStream_t st) mutable { return run_conv(l, st); });
+            emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, LC_CONV_DGRAD,
+                 conv_flops(op) * grad_ch / cin_total / launches);
           }
         }
         release_consumed();
@@ -1183,6 +1207,7 @@ struct Engine {
         });
       }
       fwd.insert(fwd.begin(), pre.begin(), pre.end());
+      fwd_meta.insert(fwd_meta.begin(), pre.size(), LaunchMeta{LC_OTHER, 0.0});
     }
     return 0;
   }
@@ -1207,6 +1232,8 @@ struct Engine {
     gfree.clear();
     fwd.clear();
     bwd.clear();
+    fwd_meta.clear();
+    bwd_meta.clear();
     tape.clear();
     f32_zero.clear();
     release_after.clear();
@@ -1341,6 +1368,49 @@ int refid_backward(refid_handle h, const float* grad_out, void* stream) {
   REFID_CUDA_CHECK(cudaMemsetAsync(e->gflat, 0, (size_t)e->flat_floats * 4, st));
   for (auto& l : e->bwd)
     if (l(st)) return 1;
+  return 0;
+}
+
+// Re-runs forward (+ backward) of the current plan on the last call's tensors with a CUDA event pair around every
+// launch and sums device time, launch count and algorithmic FLOPs per launch class
+// (0 conv forward tap-GEMM, 1 data-gradient tap-GEMM, 2 weight-gradient GEMM, 3 memory-bound kernels / memsets).
+int refid_profile(refid_handle h, int with_backward, double* ms, double* flops, long* launches, void* stream) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(e->planned && e->io_x && e->io_out, "refid_profile: run refid_forward first");
+  REFID_REQUIRE(!with_backward || (e->train && e->io_gout), "refid_profile: run refid_backward first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int c = 0; c < LC_COUNT; ++c) {
+    ms[c] = 0.0;
+    flops[c] = 0.0;
+    launches[c] = 0;
+  }
+  const size_t n = e->fwd.size() + (with_backward ? e->bwd.size() : 0);
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& x : ev) REFID_CUDA_CHECK(cudaEventCreate(&x));
+  size_t k = 0;
+  if (with_backward) REFID_CUDA_CHECK(cudaMemsetAsync(e->gflat, 0, (size_t)e->flat_floats * 4, st));
+  for (int pass = 0; pass < (with_backward ? 2 : 1); ++pass) {
+    auto& ls = pass ? e->bwd : e->fwd;
+    for (size_t i = 0; i < ls.size(); ++i, ++k) {
+      REFID_CUDA_CHECK(cudaEventRecord(ev[2 * k], st));
+      if (ls[i](st)) return 1;
+      REFID_CUDA_CHECK(cudaEventRecord(ev[2 * k + 1], st));
+    }
+  }
+  REFID_CUDA_CHECK(cudaStreamSynchronize(st));
+  k = 0;
+  for (int pass = 0; pass < (with_backward ? 2 : 1); ++pass) {
+    auto& ms_meta = pass ? e->bwd_meta : e->fwd_meta;
+    for (size_t i = 0; i < ms_meta.size(); ++i, ++k) {
+      float t = 0.f;
+      REFID_CUDA_CHECK(cudaEventElapsedTime(&t, ev[2 * k], ev[2 * k + 1]));
+      ms[ms_meta[i].cls] += t;
+      flops[ms_meta[i].cls] += ms_meta[i].flops;
+      launches[ms_meta[i].cls] += 1;
+    }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
   return 0;
 }
 

@@ -39,6 +39,7 @@ def _bind(L):
     L.refid_pack_weights.argtypes = [c_void_p, c_void_p, c_void_p]
     L.refid_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.refid_backward.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.refid_profile.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.refid_num_launches.argtypes = [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     L.refid_debug_tensor.argtypes = [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p)] + [ctypes.POINTER(c_int)] * 5
     L._refid_bound = True
@@ -98,6 +99,13 @@ class Engine:
     def backward(self, grad_out):
         assert grad_out.dtype == torch.float32 and grad_out.is_contiguous() and grad_out.is_cuda
         _lib.check(self.L.refid_backward(self.h, _lib.ptr(grad_out), self._stream()), "refid_backward")
+
+    def profile(self, with_backward=True):
+        """Per-class device time / algorithmic FLOPs / launch count of one forward(+backward) replay (see header)."""
+        ms, fl, n = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_long * 4)()
+        _lib.check(self.L.refid_profile(self.h, int(with_backward), ms, fl, n, self._stream()), "refid_profile")
+        names = ("conv_fwd", "conv_dgrad", "wgrad", "other")
+        return {k: {"ms": ms[i], "flops": fl[i], "launches": n[i]} for i, k in enumerate(names)}
 
     def num_launches(self):
         a, b = c_int(0), c_int(0)
