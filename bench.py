@@ -117,7 +117,8 @@ def cpu_reference_run(B, T, H, W, ic, ec, steps, warmup, sample_T=None, sample_h
     """The fp32 oracle port (oracle/refid_oracle.py) fwd + Charbonnier + bwd on the host cores."""
     import torch
     from oracle import refid_oracle as O
-    import tests.paramgen as paramgen  # deterministic O(1)-scale parameters shared with the parity tests
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import paramgen  # deterministic O(1)-scale parameters shared with the parity tests
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     Ts = sample_T or T

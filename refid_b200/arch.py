@@ -88,6 +88,14 @@ def _evr_layer(cin, c, fuse, atten):  # SimpleRecurrentThenDownAttenfusionmodifi
     return l
 
 
+def sync_flat_grad(g, group):
+    """In-place mean of the flat gradient over the data-parallel group (one all-reduce; NCCL on GPUs, gloo in tests)."""
+    import torch.distributed as dist
+    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+    g.div_(dist.get_world_size(group))
+    return g
+
+
 class _RefidFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, event, flat, mod):
@@ -115,8 +123,7 @@ class _RefidFunction(torch.autograd.Function):
         if group is not None:
             # Data parallelism: the only collective on the path is this all-reduce (mean) of the flat gradient --
             # one contiguous NCCL call over NVLink/NVSwitch instead of DDP's per-bucket reduction.
-            import torch.distributed as dist
-            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=group)
+            sync_flat_grad(g, group)
         return None, None, g.clone(), None
 
 
