@@ -1,5 +1,6 @@
 #include "convop.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace refid {
@@ -74,9 +75,91 @@ int fill_taps(int kind, int parity, TapTable* t) {
 
 }  // namespace
 
+// 4-D NHWC map whose box is the halo patch of one 8 x (16*NM) pixel tile: (64 channels, pitch_px, patch_rows, 1 image).
+static int make_patch_map(CUtensorMap* m, const ActSrc& s, int N, int H, int W, int pitch_px, int patch_rows) {
+  return make_act_map(m, s.ptr, N, H, W, s.pitch, s.C, 0, 0, 1, 64, pitch_px, patch_rows, 1);
+}
+
+// Returns 1 when the op was lowered onto the halo-conv engine, 0 when it does not qualify, -1 on error.
+static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out) {
+  if (d.kind != CK_3X3 && d.kind != CK_1X1) return 0;
+  static const int disabled = getenv("REFID_NO_HALO") ? 1 : 0;
+  if (disabled) return 0;
+  int ktot = 0;
+  for (int s = 0; s < d.nsrc; ++s) {
+    if (d.src[s].C % 64) return 0;
+    ktot += d.src[s].C;
+  }
+  if (ktot != d.w_cols) return 0;
+  int total = 0, seg = 1 << 30;
+  for (int g = 0; g < ngroups; ++g) {
+    if (groups[g].channels % 32) return 0;
+    total += groups[g].channels;
+    int c = groups[g].channels & -groups[g].channels;  // largest power of two dividing the group
+    if (c < seg) seg = c;
+  }
+  int BN = 256;
+  while (BN > 32 && total % BN) BN >>= 1;
+  if (total % BN) return 0;
+  if (seg > BN) seg = BN;
+  if (BN % seg || (total / seg) > kMaxNBlocks) return 0;
+  HaloConvParams& h = out->hp;
+  memset(&h, 0, sizeof(h));
+  h.num_taps = d.kind == CK_3X3 ? 9 : 1;
+  h.halo = d.kind == CK_3X3 ? 1 : 0;
+  static const int pitch3 = getenv("REFID_HALO_PITCH") ? atoi(getenv("REFID_HALO_PITCH")) : 10;
+  h.pitch_px = h.halo ? pitch3 : 8;
+  static const int bo_mode = getenv("REFID_HALO_BO") ? atoi(getenv("REFID_HALO_BO")) : 0;
+  h.bo_mode = bo_mode;
+  h.wrows_per_tap = d.wrows_per_tap;
+  h.w_row0 = d.w_row0;
+  h.nsrc = d.nsrc;
+  for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / 64;
+  h.n_blocks = total / BN;
+  h.epi_seg = seg;
+  h.N = d.N;
+  h.H = d.H;
+  h.W = d.W;
+  int NM = (2 * 2 * BN <= 512 && d.H > 16) ? 2 : 1;
+  if (!haloconv_plan(&h, BN, NM)) {
+    NM = 1;
+    if (!haloconv_plan(&h, BN, NM)) return 0;
+  }
+  h.tiles_x = (d.W + 7) / 8;
+  h.tiles_y = (d.H + 16 * NM - 1) / (16 * NM);
+  h.num_items = h.tiles_x * h.tiles_y * d.N * h.n_blocks;
+  for (int s = 0; s < d.nsrc; ++s)
+    if (make_patch_map(&h.tmA[s], d.src[s], d.N, d.H, d.W, h.pitch_px, h.patch_rows)) return -1;
+  if (make_mat_map(&h.tmB, d.w, d.w_rows, d.w_cols, 64, BN)) return -1;
+  int nd = 0;
+  for (int g = 0; g < ngroups; ++g)
+    for (int c = 0; c < groups[g].channels; c += seg) {
+      EpiDesc e = groups[g].epi;
+      e.coff += c;
+      e.osy = e.osx = 1;
+      e.ooy = e.oox = 0;
+      e.OH = d.H;
+      e.OW = d.W;
+      h.epi[nd++] = e;
+    }
+  out->use_halo = 1;
+  out->BN = BN;
+  out->BK = 64;
+  out->NM = NM;
+  out->n_blocks = h.n_blocks;
+  return 1;
+}
+
 int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out) {
   TapTable tt;
   if (fill_taps(d.kind, d.parity, &tt)) return 1;
+  out->use_halo = 0;
+  out->NM = 1;
+  {
+    const int r = try_build_halo(d, groups, ngroups, out);
+    if (r < 0) return 1;
+    if (r > 0) return 0;
+  }
   TapGemmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   REFID_REQUIRE(d.nsrc == 1 || (d.nsrc == 2 && !tt.parity_mode), "build_conv: dual source not allowed with parity views");

@@ -1,5 +1,6 @@
 // Host-side description of one convolution-shaped op and its lowering onto the tap-GEMM / wgrad kernels.
 #pragma once
+#include "haloconv.cuh"
 #include "tapgemm.cuh"
 #include "wgrad.cuh"
 
@@ -43,9 +44,16 @@ struct ConvDesc {
 struct TapGemmLaunch {
   TapGemmParams p;
   int BN, BK, n_blocks;
+  int use_halo;  // stride-1 3x3 / 1x1 with 64-channel-multiple sources run on the halo-conv engine
+  int NM;
+  HaloConvParams hp;
+  EpiDesc* epi(int i) { return use_halo ? &hp.epi[i] : &p.epi[i]; }
+  int num_epi() const { return use_halo ? hp.n_blocks * (BN / hp.epi_seg) : n_blocks; }
 };
 int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out);
-inline int run_conv(TapGemmLaunch& l, cudaStream_t s) { return launch_tapgemm(l.p, l.BN, l.BK, l.n_blocks, s); }
+inline int run_conv(TapGemmLaunch& l, cudaStream_t s) {
+  return l.use_halo ? launch_haloconv(l.hp, l.BN, l.NM, s) : launch_tapgemm(l.p, l.BN, l.BK, l.n_blocks, s);
+}
 
 struct WgradLaunch {
   WgradParams p;

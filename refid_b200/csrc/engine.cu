@@ -576,7 +576,7 @@ struct Engine {
         Engine* self = this;
         const long toff = op.nchw_toff;
         emit([l, self, toff](cudaStream_t st) mutable {
-          for (int i = 0; i < l.n_blocks; ++i) l.p.epi[i].out_nchw = self->io_out + toff;
+          for (int i = 0; i < l.num_epi(); ++i) l.epi(i)->out_nchw = self->io_out + toff;
           return run_conv(l, st);
         }, LC_CONV_FWD, conv_flops(op));
       } else {

@@ -1,0 +1,281 @@
+// Halo-conv kernel (see haloconv.cuh).  sm_100a: TMA halo patch -> shifted UMMA descriptors -> TMEM (double buffered)
+// -> epilogue warps; persistent over tiles.
+#include "haloconv.cuh"
+
+#include <stdlib.h>
+
+namespace refid {
+
+namespace {
+
+constexpr int kHaloThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
+constexpr int kHaloMaxStages = 8;
+
+// Shared-memory matrix descriptor with the swizzle base offset (bits 49-51): required when the start address is not
+// aligned to the 1024-byte swizzle repeat, which is exactly what a tap shifted by dx pixel rows produces.
+__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, int mode) {
+  uint64_t d = make_smem_desc(saddr, 16, sbo_bytes, 2u);
+  if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  if (mode == 2) d |= (uint64_t)((8u - ((saddr >> 7) & 7u)) & 7u) << 49;
+  return d;
+}
+
+template <int BN, int NM>
+__global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
+  constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
+  constexpr uint32_t B_TILE = BN * 128;        // bytes of one (tap, 64-channel slab) weight tile
+  constexpr uint32_t ACC_COLS = NM * BN;       // TMEM columns of one accumulator buffer
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) <= 32 ? 32 : ((2 * ACC_COLS) <= 64 ? 64 : ((2 * ACC_COLS) <= 128 ? 128 : ((2 * ACC_COLS) <= 256 ? 256 : 512)));
+  static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int SA = p.stages_a, SB = p.stages_b;
+  const uint32_t a_tx = (uint32_t)p.patch_rows * p.pitch_px * 128u;
+  const uint32_t a_bytes = (a_tx + 1023u) & ~1023u;
+  const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)SA * a_bytes;
+  const size_t b_total = p.resident_b ? (size_t)total_slabs * p.num_taps * B_TILE : (size_t)SB * B_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + b_total);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kHaloMaxStages;
+  uint64_t* b_full = a_empty + kHaloMaxStages;
+  uint64_t* b_empty = b_full + kHaloMaxStages;
+  uint64_t* acc_full = b_empty + kHaloMaxStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* wres_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHaloMaxStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    mbar_init(wres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmA[0]);
+      tma_prefetch_desc(&p.tmB);
+      if (p.resident_b) {
+        mbar_arrive_expect_tx(wres_bar, (uint32_t)b_total);
+        for (int ks = 0; ks < total_slabs; ++ks)
+          for (int tap = 0; tap < p.num_taps; ++tap)
+            tma_load_2d(b_base + (size_t)(ks * p.num_taps + tap) * B_TILE, &p.tmB, wres_bar, ks * 64,
+                        p.w_row0 + tap * p.wrows_per_tap);
+      }
+      uint32_t ia = 0, ib = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
+        const int x0 = (tile % p.tiles_x) * 8;
+        const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
+        const int n = tile / tiles_per_img;
+        int ks = 0;
+        for (int src = 0; src < p.nsrc; ++src) {
+          for (int slab = 0; slab < p.src_slabs[src]; ++slab, ++ks) {
+            const int sa = ia % SA;
+            mbar_wait(&a_empty[sa], ((ia / SA) & 1) ^ 1, 0x700 + sa);
+            mbar_arrive_expect_tx(&a_full[sa], a_tx);
+            tma_load_4d(a_base + (size_t)sa * a_bytes, &p.tmA[src], &a_full[sa], slab * 64, x0 - p.halo, y0 - p.halo, n);
+            ++ia;
+            if (!p.resident_b) {
+              for (int tap = 0; tap < p.num_taps; ++tap) {
+                const int sb = ib % SB;
+                mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1, 0x710 + sb);
+                mbar_arrive_expect_tx(&b_full[sb], B_TILE);
+                tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * 64,
+                            p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
+                ++ib;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (p.resident_b) {
+        mbar_wait(wres_bar, 0, 0x720);
+        tc_fence_after();
+      }
+      const uint32_t sbo = (uint32_t)p.pitch_px * 128u;
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x730 + buf);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * ACC_COLS;
+        for (int ks = 0; ks < total_slabs; ++ks) {
+          const int sa = ia % SA;
+          mbar_wait(&a_full[sa], (ia / SA) & 1, 0x740 + sa);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_base + (size_t)sa * a_bytes);
+          for (int tap = 0; tap < p.num_taps; ++tap) {
+            const int dy = p.num_taps == 9 ? tap / 3 - 1 : 0, dx = p.num_taps == 9 ? tap % 3 - 1 : 0;
+            const uint32_t tap_off = (uint32_t)((dy + p.halo) * p.pitch_px + dx + p.halo) * 128u;
+            uint32_t b_addr;
+            int sb = 0;
+            if (p.resident_b) {
+              b_addr = smem_u32(b_base + (size_t)(ks * p.num_taps + tap) * B_TILE);
+            } else {
+              sb = ib % SB;
+              mbar_wait(&b_full[sb], (ib / SB) & 1, 0x750 + sb);
+              tc_fence_after();
+              b_addr = smem_u32(b_base + (size_t)sb * B_TILE);
+            }
+#pragma unroll
+            for (int j = 0; j < NM; ++j) {
+              const uint32_t aj = a_addr + tap_off + (uint32_t)j * 16u * sbo;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = make_smem_desc_bo(aj + k * 32, sbo, p.bo_mode);
+                const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, 2u);
+                umma_bf16(acc + j * BN, ad, bd, IDESC, (ks > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            if (!p.resident_b) {
+              umma_commit(&b_empty[sb]);
+              ++ib;
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          ++ia;
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global, overlapped with the next item's MMAs ----------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
+      const int x = (tile % p.tiles_x) * 8 + tx;
+      const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
+      const int n = tile / tiles_per_img;
+      const uint32_t buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < NM; ++j) {
+        const int y = y0 + j * 16 + ty;
+        const bool valid = (y < p.H) && (x < p.W);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c0), v);
+          tmem_ld_wait();
+          if (valid) {
+            const int ch = nblk * BN + c0;
+            const EpiDesc& e = p.epi[ch / p.epi_seg];
+            const size_t pix = ((size_t)n * e.OH + (size_t)y) * e.OW + (size_t)x;
+            const size_t base = pix * (size_t)e.C + e.coff;
+            epi_apply16(e, v, e.bias, base, ch % p.epi_seg, n, y, x);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+constexpr size_t kHaloSmemMax = 227 * 1024;
+constexpr size_t kHaloBarBytes = (4 * kHaloMaxStages + 5) * sizeof(uint64_t) + 16;
+
+size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
+  const size_t a_bytes = ((size_t)p.patch_rows * p.pitch_px * 128 + 1023) & ~(size_t)1023;
+  const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
+  const size_t b_total = p.resident_b ? (size_t)total_slabs * p.num_taps * BN * 128 : (size_t)p.stages_b * BN * 128;
+  return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + 1024;
+}
+
+template <int BN, int NM>
+int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
+    configured = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    REFID_CUDA_CHECK(cudaGetDevice(&dev));
+    REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  haloconv_kernel<BN, NM><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int haloconv_plan(HaloConvParams* p, int BN, int NM) {
+  if (2 * NM * BN > 512) return 0;
+  p->patch_rows = 16 * NM + 2 * p->halo;
+  const int total_slabs = p->src_slabs[0] + (p->nsrc > 1 ? p->src_slabs[1] : 0);
+  // weights resident for the whole kernel when they fit next to >= 2 activation stages
+  if (p->n_blocks == 1) {
+    p->resident_b = 1;
+    p->stages_b = 0;
+    for (int sa = total_slabs >= 3 ? 3 : 2; sa >= 2; --sa) {
+      p->stages_a = sa;
+      if (halo_smem_bytes(*p, BN) <= kHaloSmemMax) return 1;
+    }
+  }
+  p->resident_b = 0;
+  p->stages_a = 2;
+  for (int sb = kHaloMaxStages; sb >= 3; --sb) {
+    p->stages_b = sb;
+    if (halo_smem_bytes(*p, BN) <= kHaloSmemMax) {
+      p->stages_a = 3;
+      if (halo_smem_bytes(*p, BN) > kHaloSmemMax) p->stages_a = 2;
+      return 1;
+    }
+  }
+  return 0;
+}
+
+int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream) {
+#define HINST(bn, nm) \
+  if (BN == bn && NM == nm) return launch_halo_inst<bn, nm>(p, stream);
+  HINST(32, 1) HINST(64, 1) HINST(128, 1) HINST(256, 1)
+  HINST(32, 2) HINST(64, 2) HINST(128, 2)
+#undef HINST
+  set_error("haloconv: unsupported BN=%d NM=%d", BN, NM);
+  return 1;
+}
+
+}  // namespace refid

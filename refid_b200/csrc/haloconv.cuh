@@ -1,0 +1,42 @@
+// Halo-conv: persistent, halo-reusing implicit-GEMM engine for the stride-1 3x3 / 1x1 convolutions (forward and
+// data-gradient) that carry ~90 % of the network's FLOPs.
+//
+// Why a second engine: the tap-GEMM kernel (tapgemm.cuh) fetches one 128 x BK activation tile PER TAP from L2, i.e. 9x
+// the input for a 3x3 conv.  At N = Cout = 64 a 128x64x16 MMA takes 32 cycles, so the tensor pipe wants 128 B/clk/SM of
+// A operand while the L2 can deliver ~42 B/clk/SM (6300 B/clk chip-wide): the kernel is L2-bound at ~1/3 of peak before
+// any fixed cost.  Here ONE (TH+2) x (TW+2) halo patch per 64-channel K slab is staged in shared memory by a single TMA
+// box load (zero fill = padding) and all nine taps are issued from it with shifted UMMA descriptors (start address moved
+// by whole 128-byte pixel rows; the swizzle phase is carried in the descriptor's base-offset field).  The kernel is
+// persistent (one CTA per SM loops over tiles), accumulators are double-buffered in TMEM so the epilogue of tile i
+// overlaps the MMAs of tile i+1, weights are either resident in shared memory for the whole kernel (C = 64 layers) or
+// streamed tap by tap through their own ring, and one CTA iteration can process two vertically adjacent pixel tiles
+// (M = 256) against the same weight tiles.
+#pragma once
+#include "tapgemm.cuh"
+
+namespace refid {
+
+struct HaloConvParams {
+  CUtensorMap tmA[2];  // per source: dims (C, W, H, N), box (64, pitch_px, patch_rows, 1), 128B swizzle
+  CUtensorMap tmB;     // packed weights [rows][K], box (64, BN)
+  EpiDesc epi[kMaxNBlocks];
+  int epi_seg;      // output channels per EpiDesc (divides BN)
+  int num_taps;     // 9 or 1
+  int halo;         // 1 (3x3) or 0 (1x1)
+  int pitch_px;     // pixels per patch row in shared memory (multiple of 8)
+  int patch_rows;   // 16*NM + 2*halo
+  int wrows_per_tap, w_row0;
+  int nsrc, src_slabs[2];
+  int n_blocks;
+  int tiles_x, tiles_y, N, H, W;  // tiles are 8 wide x 16*NM high
+  int num_items;                  // tiles * n_blocks
+  int resident_b;                 // weights stay in shared memory for the whole kernel (n_blocks == 1)
+  int stages_a, stages_b;
+  int bo_mode;  // experiment switch: how the swizzle base offset of shifted A descriptors is formed
+};
+
+int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);
+// Shared-memory plan; returns 0 when the configuration does not fit.
+int haloconv_plan(HaloConvParams* p, int BN, int NM);
+
+}  // namespace refid

@@ -2,6 +2,7 @@
 #include <string.h>
 #include "common.cu"
 #include "tapgemm.cu"
+#include "haloconv.cu"
 #include "wgrad.cu"
 #include "convop.cu"
 #include "elementwise.cu"

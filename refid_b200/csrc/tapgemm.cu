@@ -32,6 +32,76 @@ __device__ __forceinline__ void store16(__nv_bfloat16* p, const float* f) {
   q[1] = b;
 }
 
+// Epilogue of 16 consecutive output channels [c0, c0+16) of one pixel (see EpiDesc in tapgemm.cuh).
+__device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const float* bias, size_t base, int c0, int n, int y,
+                                            int x) {
+  if (bias) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(bias + e.coff + c0 + i);
+  }
+  if (e.pre) {
+    float t[16];
+    load16(e.pre + base + c0, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+  if (e.pre2) {
+    float t[16];
+    load16(e.pre2 + base + c0, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+  if (e.sv) {
+    float t[16];
+    load16(e.sv + base + c0, t);
+    if (e.act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= gelu_grad_f(t[i]);
+    } else {
+      const float sl = e.slope;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= (t[i] > 0.f ? 1.f : sl);
+    }
+  } else {
+    if (e.out_pre) store16(e.out_pre + base + c0, v);
+    if (e.act == ACT_LRELU) {
+      const float sl = e.slope;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+    } else if (e.act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
+    }
+  }
+  if (e.out) store16(e.out + base + c0, v);
+  if (e.out_nchw && c0 == 0) {
+    float* o = e.out_nchw + (size_t)n * e.nchw_nstride + (size_t)(y * e.osy + e.ooy) * e.OW + (size_t)(x * e.osx + e.oox);
+    const size_t plane = (size_t)e.OH * e.OW;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < e.nchw_C) o[i * plane] = v[i];
+  }
+  if (e.out_f32) {
+    float4* o = reinterpret_cast<float4*>(e.out_f32 + base + c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 t = o[i];
+      t.x += v[4 * i];
+      t.y += v[4 * i + 1];
+      t.z += v[4 * i + 2];
+      t.w += v[4 * i + 3];
+      o[i] = t;
+    }
+  }
+  if (e.out2) {
+    float t[16];
+    load16(e.post + base + c0, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] += v[i];
+    store16(e.out2 + base + c0, t);
+  }
+}
+
 template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   constexpr int A_BYTES = 128 * BK * 2;
@@ -141,73 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (valid) {
-        if (bias) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(bias + e.coff + c0 + i);
-        }
-        if (e.pre) {
-          float t[16];
-          load16(e.pre + base + c0, t);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += t[i];
-        }
-        if (e.pre2) {
-          float t[16];
-          load16(e.pre2 + base + c0, t);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += t[i];
-        }
-        if (e.sv) {
-          float t[16];
-          load16(e.sv + base + c0, t);
-          if (e.act == ACT_GELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= gelu_grad_f(t[i]);
-          } else {
-            const float sl = e.slope;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= (t[i] > 0.f ? 1.f : sl);
-          }
-        } else {
-          if (e.out_pre) store16(e.out_pre + base + c0, v);
-          if (e.act == ACT_LRELU) {
-            const float sl = e.slope;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
-          } else if (e.act == ACT_GELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
-          }
-        }
-        if (e.out) store16(e.out + base + c0, v);
-        if (e.out_nchw && c0 == 0) {
-          float* o = e.out_nchw + (size_t)n * e.nchw_nstride + (size_t)(y * e.osy + e.ooy) * e.OW + (size_t)(x * e.osx + e.oox);
-          const size_t plane = (size_t)e.OH * e.OW;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (i < e.nchw_C) o[i * plane] = v[i];
-        }
-        if (e.out_f32) {
-          float4* o = reinterpret_cast<float4*>(e.out_f32 + base + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 t = o[i];
-            t.x += v[4 * i];
-            t.y += v[4 * i + 1];
-            t.z += v[4 * i + 2];
-            t.w += v[4 * i + 3];
-            o[i] = t;
-          }
-        }
-        if (e.out2) {
-          float t[16];
-          load16(e.post + base + c0, t);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) t[i] += v[i];
-          store16(e.out2 + base + c0, t);
-        }
-      }
+      if (valid) epi_apply16(e, v, bias, base, c0, n, y, x);
     }
   }
 
