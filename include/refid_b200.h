@@ -78,6 +78,9 @@ int refid_backward(refid_handle h, const float* grad_out, void* stream);
  * [0] conv forward tap-GEMM, [1] data-gradient tap-GEMM, [2] weight-gradient GEMM, [3] memory-bound kernels. */
 int refid_profile(refid_handle h, int with_backward, double ms[4], double flops[4], long launches[4], void* stream);
 
+/* Same replay, one CSV row per launch (pass,index,class,label,ms,gflop) written to `path`. */
+int refid_profile_csv(refid_handle h, int with_backward, const char* path, void* stream);
+
 /* Introspection used by tests and profiling. */
 int refid_num_launches(refid_handle h, int* fwd, int* bwd);
 /* Device pointer + shape of a named intermediate activation (NHWC bf16, `pitch` channels per pixel). */

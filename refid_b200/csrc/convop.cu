@@ -107,10 +107,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   memset(&h, 0, sizeof(h));
   h.num_taps = d.kind == CK_3X3 ? 9 : 1;
   h.halo = d.kind == CK_3X3 ? 1 : 0;
-  static const int pitch3 = getenv("REFID_HALO_PITCH") ? atoi(getenv("REFID_HALO_PITCH")) : 10;
-  h.pitch_px = h.halo ? pitch3 : 8;
-  static const int bo_mode = getenv("REFID_HALO_BO") ? atoi(getenv("REFID_HALO_BO")) : 0;
-  h.bo_mode = bo_mode;
+  h.pitch_px = h.halo ? 10 : 8;
   h.wrows_per_tap = d.wrows_per_tap;
   h.w_row0 = d.w_row0;
   h.nsrc = d.nsrc;

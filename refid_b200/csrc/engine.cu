@@ -83,6 +83,7 @@ enum LaunchClass { LC_CONV_FWD = 0, LC_CONV_DGRAD = 1, LC_WGRAD = 2, LC_OTHER = 
 struct LaunchMeta {
   int cls;
   double flops;  // algorithmic FLOPs (2*MAC on un-padded channel counts); 0 for memory-bound kernels
+  std::string label;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -342,10 +343,11 @@ struct Engine {
     tens[id].goff = (long)gbufs[tens[id].gidx].off;
   }
 
-  void emit(Launch l, int cls = LC_OTHER, double flops = 0.0) {
+  std::string cur_label;  // site / op the launches being emitted belong to (profiling only)
+  void emit(Launch l, int cls = LC_OTHER, double flops = 0.0, const char* tag = "") {
     if (dry) return;
     cur->push_back(std::move(l));
-    (cur == &fwd ? fwd_meta : bwd_meta).push_back(LaunchMeta{cls, flops});
+    (cur == &fwd ? fwd_meta : bwd_meta).push_back(LaunchMeta{cls, flops, cur_label + tag});
   }
 
   // algorithmic FLOPs of one convolution (forward = data-gradient = weight-gradient)
@@ -402,7 +404,7 @@ struct Engine {
       a.dst_acc = tens[id].gwritten ? 1 : 0;
       a.n = tens[id].elems();
       tens[id].gwritten = true;
-      emit([a](cudaStream_t s) { return launch_addmask(a, s); });
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, "addmask");
       gunref(g0);
       gunref(g1);
     }
@@ -448,7 +450,7 @@ struct Engine {
       a.dstf = PF(tens[id].gfoff);
       a.n = tens[id].elems();
       tens[id].gfwritten = true;
-      emit([a](cudaStream_t s) { return launch_addmask(a, s); });
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, "addmask");
       return 0;
     }
     gbufs[src_gidx].refs++;
@@ -482,7 +484,7 @@ struct Engine {
       a.dst = P(tens[id].goff);
       a.n = tens[id].elems();
       tens[id].gwritten = true;
-      emit([a](cudaStream_t s) { return launch_addmask(a, s); });
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, "addmask");
       *gz = P(tens[id].goff);
       return 0;
     }
@@ -524,6 +526,7 @@ struct Engine {
     }
     if (op.post >= 0 && op.out2 < 0) op.out2 = new_tensor(in0.N, oh, ow, cout, name.empty() ? "" : name + "+");
     if (!dry) {
+      cur_label = s.key;
       ConvDesc d;
       memset(&d, 0, sizeof(d));
       d.kind = op.kind;
@@ -578,9 +581,9 @@ struct Engine {
         emit([l, self, toff](cudaStream_t st) mutable {
           for (int i = 0; i < l.num_epi(); ++i) l.epi(i)->out_nchw = self->io_out + toff;
           return run_conv(l, st);
-        }, LC_CONV_FWD, conv_flops(op));
+        }, LC_CONV_FWD, conv_flops(op), ":fwd");
       } else {
-        emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, LC_CONV_FWD, conv_flops(op));
+        emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, LC_CONV_FWD, conv_flops(op), ":fwd");
       }
     }
     if (train && !op.no_tape) {
@@ -591,12 +594,13 @@ struct Engine {
   }
 
   int emit_colsum(const __nv_bfloat16* gz, long rows, int C, float* dst) {
-    emit([gz, rows, C, dst](cudaStream_t s) { return launch_colsum(gz, rows, C, dst, s); });
+    emit([gz, rows, C, dst](cudaStream_t s) { return launch_colsum(gz, rows, C, dst, s); }, LC_OTHER, 0.0, ":colsum");
     return 0;
   }
 
   int conv_bwd(const ConvOp& op) {
     const Site& s = sites[op.site];
+    cur_label = "";
     if (op.out2 >= 0) {
       const __nv_bfloat16* gs = nullptr;
       if (finalize(op.out2, &gs)) return 1;
@@ -611,6 +615,7 @@ struct Engine {
     const __nv_bfloat16* gz = nullptr;
     if (finalize(op.out, &gz)) return 1;
     if (!gz) return 0;
+    cur_label = s.key;
     const Ten o = tens[op.out];
     const Ten in0 = tens[op.in[0]];
     const int cout = o.C;
@@ -648,7 +653,7 @@ struct Engine {
       }
       WgradLaunch wl;
       if (build_wgrad(d, q, gflat + s.w_off, &wl)) return 1;
-      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, conv_flops(op));
+      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, conv_flops(op), ":wgrad");
     }
     // data gradient
     if (s.dgrad_off >= 0) {
@@ -712,12 +717,13 @@ struct Engine {
             TapGemmLaunch l;
             if (build_conv(d, groups, ng, &l)) return 1;
             emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, LC_CONV_DGRAD,
-                 conv_flops(op) * grad_ch / cin_total / launches);
+                 conv_flops(op) * grad_ch / cin_total / launches, ":dgrad");
           }
         }
         release_consumed();
       }
     }
+    cur_label = "";
     if (op.res >= 0) add_pending(op.res, tens[op.out].gidx, tens[op.out].goff);
     if (op.res2 >= 0) add_pending(op.res2, tens[op.out].gidx, tens[op.out].goff);
     release_grad(op.out);
@@ -734,7 +740,8 @@ struct Engine {
     {
       const __nv_bfloat16 *px = P(tx.off);
       __nv_bfloat16* py = P(tens[y].off);
-      emit([px, py, npix](cudaStream_t s) { return launch_ln_fwd(px, py, npix, s); });
+      cur_label = "";
+      emit([px, py, npix](cudaStream_t s) { return launch_ln_fwd(px, py, npix, s); }, LC_OTHER, 0.0, "ln_fwd");
     }
     if (train) {
       Engine* self = this;
@@ -751,7 +758,7 @@ struct Engine {
         const __nv_bfloat16* px = self->P(self->tens[x].off);
         self->emit([px, gy, t, npix](cudaStream_t s) {
           return launch_ln_bwd(px, gy, t.pre2, t.dst, t.pre ? 1 : 0, t.dstf, npix, s);
-        });
+        }, LC_OTHER, 0.0, "ln_bwd");
         self->release_consumed();
         self->release_grad(y);
         return 0;
@@ -773,7 +780,7 @@ struct Engine {
       const float *w = wmaster + s.w_off, *b = wmaster + s.b_off;
       float* pool = pool_off >= 0 ? PF(pool_off) : nullptr;
       const int N = ta.N, Hh = ta.H, Ww = ta.W;
-      emit([pa, w, b, pd, pg, pool, N, Hh, Ww](cudaStream_t st) { return launch_dw_fwd(pa, w, b, pd, pg, pool, N, Hh, Ww, st); });
+      emit([pa, w, b, pd, pg, pool, N, Hh, Ww](cudaStream_t st) { return launch_dw_fwd(pa, w, b, pd, pg, pool, N, Hh, Ww, st); }, LC_OTHER, 0.0, "dw_fwd");
     }
     if (train) {
       Engine* self = this;
@@ -789,7 +796,7 @@ struct Engine {
         const float* w = self->wmaster + s.w_off;
         float *gw = self->gflat + s.w_off, *gb = self->gflat + s.b_off;
         const int N = ta.N, Hh = ta.H, Ww = ta.W;
-        self->emit([gz, pa, w, ga, gw, gb, N, Hh, Ww](cudaStream_t st) { return launch_dw_bwd(gz, pa, w, ga, gw, gb, N, Hh, Ww, st); });
+        self->emit([gz, pa, w, ga, gw, gb, N, Hh, Ww](cudaStream_t st) { return launch_dw_bwd(gz, pa, w, ga, gw, gb, N, Hh, Ww, st); }, LC_OTHER, 0.0, "dw_bwd");
         self->release_grad(g);
         return 0;
       });
@@ -840,8 +847,8 @@ struct Engine {
       float *pool = PF(pool_off), *sg = PF(s_off), *mean = PF(mean_off), *z = PF(z_off);
       const __nv_bfloat16 *pgi = P(tens[g_i].off), *pge = P(tens[g_e].off);
       __nv_bfloat16* pcs = P(tens[cs].off);
-      emit([pool, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, inv_hw, sp, sg, mean, z, N, st); });
-      emit([pgi, pge, sg, pcs, N, hw](cudaStream_t st) { return launch_gate_fwd(pgi, pge, sg, pcs, N, hw, st); });
+      emit([pool, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, inv_hw, sp, sg, mean, z, N, st); }, LC_OTHER, 0.0, "se_fwd");
+      emit([pgi, pge, sg, pcs, N, hw](cudaStream_t st) { return launch_gate_fwd(pgi, pge, sg, pcs, N, hw, st); }, LC_OTHER, 0.0, "gate_fwd");
     }
     if (train) {
       Engine* self = this;
@@ -862,13 +869,13 @@ struct Engine {
           REFID_CUDA_CHECK(cudaMemsetAsync(gs, 0, (size_t)N * 64 * 4, st));
           return 0;
         });
-        self->emit([gcs, pgi, pge, gs, N, hw](cudaStream_t st) { return launch_gate_bwd_reduce(gcs, pgi, pge, gs, N, hw, st); });
+        self->emit([gcs, pgi, pge, gs, N, hw](cudaStream_t st) { return launch_gate_bwd_reduce(gcs, pgi, pge, gs, N, hw, st); }, LC_OTHER, 0.0, "gate_bwd_reduce");
         self->emit([gs, sg, mean, z, inv_hw, sp, gpool, N](cudaStream_t st) {
           return launch_se_bwd(gs, sg, mean, z, inv_hw, sp, gpool, N, st);
-        });
+        }, LC_OTHER, 0.0, "se_bwd");
         self->emit([gcs, sg, gpool, pde, gi_f32, gz_de, N, hw](cudaStream_t st) {
           return launch_gate_bwd_apply(gcs, sg, gpool, pde, gi_f32, gz_de, N, hw, st);
-        });
+        }, LC_OTHER, 0.0, "gate_bwd_apply");
         self->release_grad(cs);
         return 0;
       });
@@ -947,7 +954,7 @@ struct Engine {
     {
       __nv_bfloat16* o = P(tens[ximg].off);
       const int Bc = B, Cin = cfg.img_chn, Hh = H, Ww = W, Kp = Kp_img;
-      emit([self, o, Bc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_x, o, Bc, 1, Cin, Hh, Ww, Kp, st); });
+      emit([self, o, Bc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_x, o, Bc, 1, Cin, Hh, Ww, Kp, st); }, LC_OTHER, 0.0, "unroll5");
     }
     ConvOp hi;
     hi.kind = CK_ROWS5;
@@ -997,7 +1004,7 @@ struct Engine {
     {
       __nv_bfloat16* o = P(tens[xev].off);
       const int Bc = B, Tc = T, Cin = cfg.ev_chn, Hh = H, Ww = W, Kp = Kp_ev;
-      emit([self, o, Bc, Tc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_ev, o, Bc, Tc, Cin, Hh, Ww, Kp, st); });
+      emit([self, o, Bc, Tc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_ev, o, Bc, Tc, Cin, Hh, Ww, Kp, st); }, LC_OTHER, 0.0, "unroll5");
     }
     ConvOp he;
     he.kind = CK_ROWS5;
@@ -1187,7 +1194,7 @@ struct Engine {
         const int Bc = self->B, Tc = self->T, Cv = self->cfg.out_chn, Hh = self->H, Ww = self->W;
         self->emit([self, dst, Bc, Tc, Cv, Hh, Ww](cudaStream_t st) {
           return launch_gout_pack(self->io_gout, dst, Bc, Tc, Cv, Hh, Ww, st);
-        });
+        }, LC_OTHER, 0.0, "gout_pack");
         ConvOp op;
         op.site = ps;
         op.in[0] = sp_all;
@@ -1207,7 +1214,7 @@ struct Engine {
         });
       }
       fwd.insert(fwd.begin(), pre.begin(), pre.end());
-      fwd_meta.insert(fwd_meta.begin(), pre.size(), LaunchMeta{LC_OTHER, 0.0});
+      fwd_meta.insert(fwd_meta.begin(), pre.size(), LaunchMeta{LC_OTHER, 0.0, "memset:state0"});
     }
     return 0;
   }
@@ -1410,6 +1417,44 @@ int refid_profile(refid_handle h, int with_backward, double* ms, double* flops, 
       launches[ms_meta[i].cls] += 1;
     }
   }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return 0;
+}
+
+// Same replay as refid_profile, one CSV row per launch: pass,index,class,label,ms,gflop.
+int refid_profile_csv(refid_handle h, int with_backward, const char* path, void* stream) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(e->planned && e->io_x && e->io_out, "refid_profile_csv: run refid_forward first");
+  REFID_REQUIRE(!with_backward || (e->train && e->io_gout), "refid_profile_csv: run refid_backward first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = e->fwd.size() + (with_backward ? e->bwd.size() : 0);
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& x : ev) REFID_CUDA_CHECK(cudaEventCreate(&x));
+  size_t k = 0;
+  if (with_backward) REFID_CUDA_CHECK(cudaMemsetAsync(e->gflat, 0, (size_t)e->flat_floats * 4, st));
+  for (int pass = 0; pass < (with_backward ? 2 : 1); ++pass) {
+    auto& ls = pass ? e->bwd : e->fwd;
+    for (size_t i = 0; i < ls.size(); ++i, ++k) {
+      REFID_CUDA_CHECK(cudaEventRecord(ev[2 * k], st));
+      if (ls[i](st)) return 1;
+      REFID_CUDA_CHECK(cudaEventRecord(ev[2 * k + 1], st));
+    }
+  }
+  REFID_CUDA_CHECK(cudaStreamSynchronize(st));
+  FILE* f = fopen(path, "w");
+  REFID_REQUIRE(f != nullptr, "refid_profile_csv: cannot open %s", path);
+  fprintf(f, "pass,index,class,label,ms,gflop\n");
+  k = 0;
+  for (int pass = 0; pass < (with_backward ? 2 : 1); ++pass) {
+    auto& mm = pass ? e->bwd_meta : e->fwd_meta;
+    for (size_t i = 0; i < mm.size(); ++i, ++k) {
+      float t = 0.f;
+      REFID_CUDA_CHECK(cudaEventElapsedTime(&t, ev[2 * k], ev[2 * k + 1]));
+      fprintf(f, "%s,%zu,%d,%s,%.6f,%.6f\n", pass ? "bwd" : "fwd", i, mm[i].cls, mm[i].label.c_str(), t, mm[i].flops * 1e-9);
+    }
+  }
+  fclose(f);
   for (auto& x : ev) cudaEventDestroy(x);
   return 0;
 }

@@ -11,32 +11,35 @@ namespace {
 constexpr int kHaloThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
 constexpr int kHaloMaxStages = 8;
 
-// Shared-memory matrix descriptor with the swizzle base offset (bits 49-51): required when the start address is not
-// aligned to the 1024-byte swizzle repeat, which is exactly what a tap shifted by dx pixel rows produces.
-__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, int mode) {
-  uint64_t d = make_smem_desc(saddr, 16, sbo_bytes, 2u);
-  if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-  if (mode == 2) d |= (uint64_t)((8u - ((saddr >> 7) & 7u)) & 7u) << 49;
-  return d;
-}
-
-template <int BN, int NM>
+// Shifted taps: a tap (dy,dx) only moves the START ADDRESS of the A descriptor by whole 128-byte pixel rows inside the halo
+// patch.  The 128B swizzle XOR is a function of the absolute shared-memory address bits on both the TMA write and the UMMA
+// read side, so no descriptor base-offset is needed (verified on B200 with tools/halo_tap_probe.py).
+//
+// Issue-rate notes (measured with tools/ubench/umma_rate.cu): an SS-mode 128xNx16 MMA never takes less than ~62.5 cycles,
+// so the single issuing thread has <= 62 cycles per MMA at N <= 128.  The producer and MMA warps therefore run their
+// loops warp-uniformly (warp index via shuffle, elect.sync only around the issue) so that descriptors live in uniform
+// registers, and every per-MMA descriptor is `base + compile-time constant` (TAPS / pitch / NM are template parameters).
+template <int BN, int NM, int TAPS>
 __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
+  constexpr int HALO = TAPS == 9 ? 1 : 0;
+  constexpr int PITCH = TAPS == 9 ? 10 : 8;       // pixels per patch row in shared memory
+  constexpr int PATCH_ROWS = 16 * NM + 2 * HALO;
   constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
   constexpr uint32_t B_TILE = BN * 128;        // bytes of one (tap, 64-channel slab) weight tile
   constexpr uint32_t ACC_COLS = NM * BN;       // TMEM columns of one accumulator buffer
   constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) <= 32 ? 32 : ((2 * ACC_COLS) <= 64 ? 64 : ((2 * ACC_COLS) <= 128 ? 128 : ((2 * ACC_COLS) <= 256 ? 256 : 512)));
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  constexpr uint32_t A_TX = (uint32_t)PATCH_ROWS * PITCH * 128u;
+  constexpr uint32_t A_BYTES = (A_TX + 1023u) & ~1023u;
+  constexpr uint32_t SBO = (uint32_t)PITCH * 128u;  // 8-pixel group (one tile row) to the next tile row
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int SA = p.stages_a, SB = p.stages_b;
-  const uint32_t a_tx = (uint32_t)p.patch_rows * p.pitch_px * 128u;
-  const uint32_t a_bytes = (a_tx + 1023u) & ~1023u;
   const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
   uint8_t* a_base = smem;
-  uint8_t* b_base = smem + (size_t)SA * a_bytes;
-  const size_t b_total = p.resident_b ? (size_t)total_slabs * p.num_taps * B_TILE : (size_t)SB * B_TILE;
+  uint8_t* b_base = smem + (size_t)SA * A_BYTES;
+  const size_t b_total = p.resident_b ? (size_t)total_slabs * TAPS * B_TILE : (size_t)SB * B_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + b_total);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kHaloMaxStages;
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
   uint64_t* wres_bar = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -75,95 +78,117 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---------------- TMA producer (whole warp runs the loop; one elected lane issues) ----------------
+    if (elect_one()) {
       tma_prefetch_desc(&p.tmA[0]);
       tma_prefetch_desc(&p.tmB);
       if (p.resident_b) {
         mbar_arrive_expect_tx(wres_bar, (uint32_t)b_total);
         for (int ks = 0; ks < total_slabs; ++ks)
-          for (int tap = 0; tap < p.num_taps; ++tap)
-            tma_load_2d(b_base + (size_t)(ks * p.num_taps + tap) * B_TILE, &p.tmB, wres_bar, ks * 64,
-                        p.w_row0 + tap * p.wrows_per_tap);
+          for (int tap = 0; tap < TAPS; ++tap)
+            tma_load_2d(b_base + (size_t)(ks * TAPS + tap) * B_TILE, &p.tmB, wres_bar, ks * 64, p.w_row0 + tap * p.wrows_per_tap);
       }
-      uint32_t ia = 0, ib = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
-        const int x0 = (tile % p.tiles_x) * 8;
-        const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
-        const int n = tile / tiles_per_img;
-        int ks = 0;
-        for (int src = 0; src < p.nsrc; ++src) {
-          for (int slab = 0; slab < p.src_slabs[src]; ++slab, ++ks) {
-            const int sa = ia % SA;
-            mbar_wait(&a_empty[sa], ((ia / SA) & 1) ^ 1, 0x700 + sa);
-            mbar_arrive_expect_tx(&a_full[sa], a_tx);
-            tma_load_4d(a_base + (size_t)sa * a_bytes, &p.tmA[src], &a_full[sa], slab * 64, x0 - p.halo, y0 - p.halo, n);
-            ++ia;
-            if (!p.resident_b) {
-              for (int tap = 0; tap < p.num_taps; ++tap) {
-                const int sb = ib % SB;
-                mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1, 0x710 + sb);
+    }
+    uint32_t ia = 0, ib = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
+      const int x0 = (tile % p.tiles_x) * 8;
+      const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
+      const int n = tile / tiles_per_img;
+      int ks = 0;
+      for (int src = 0; src < p.nsrc; ++src) {
+        for (int slab = 0; slab < p.src_slabs[src]; ++slab, ++ks) {
+          const int sa = ia % SA;
+          mbar_wait(&a_empty[sa], ((ia / SA) & 1) ^ 1, 0x700 + sa);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[sa], A_TX);
+            tma_load_4d(a_base + (size_t)sa * A_BYTES, &p.tmA[src], &a_full[sa], slab * 64, x0 - HALO, y0 - HALO, n);
+          }
+          ++ia;
+          if (!p.resident_b) {
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const int sb = ib % SB;
+              mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1, 0x710 + sb);
+              if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[sb], B_TILE);
-                tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * 64,
-                            p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
-                ++ib;
+                tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * 64, p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
               }
+              ++ib;
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      if (p.resident_b) {
-        mbar_wait(wres_bar, 0, 0x720);
+    // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    if (p.resident_b) {
+      mbar_wait(wres_bar, 0, 0x720);
+      tc_fence_after();
+    }
+    const uint32_t a_base_u = smem_u32(a_base), b_base_u = smem_u32(b_base);
+    uint32_t ia = 0, ib = 0, it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x730 + buf);
+      tc_fence_after();
+      const uint32_t acc = tm + buf * ACC_COLS;
+      for (int ks = 0; ks < total_slabs; ++ks) {
+        const int sa = ia % SA;
+        mbar_wait(&a_full[sa], (ia / SA) & 1, 0x740 + sa);
         tc_fence_after();
-      }
-      const uint32_t sbo = (uint32_t)p.pitch_px * 128u;
-      uint32_t ia = 0, ib = 0, it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const uint32_t buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x730 + buf);
-        tc_fence_after();
-        const uint32_t acc = tmem_base + buf * ACC_COLS;
-        for (int ks = 0; ks < total_slabs; ++ks) {
-          const int sa = ia % SA;
-          mbar_wait(&a_full[sa], (ia / SA) & 1, 0x740 + sa);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_base + (size_t)sa * a_bytes);
-          for (int tap = 0; tap < p.num_taps; ++tap) {
-            const int dy = p.num_taps == 9 ? tap / 3 - 1 : 0, dx = p.num_taps == 9 ? tap % 3 - 1 : 0;
-            const uint32_t tap_off = (uint32_t)((dy + p.halo) * p.pitch_px + dx + p.halo) * 128u;
-            uint32_t b_addr;
-            int sb = 0;
-            if (p.resident_b) {
-              b_addr = smem_u32(b_base + (size_t)(ks * p.num_taps + tap) * B_TILE);
-            } else {
-              sb = ib % SB;
-              mbar_wait(&b_full[sb], (ib / SB) & 1, 0x750 + sb);
-              tc_fence_after();
-              b_addr = smem_u32(b_base + (size_t)sb * B_TILE);
-            }
+        const uint64_t a_desc0 = make_smem_desc(a_base_u + (uint32_t)sa * A_BYTES, 16, SBO, 2u);
+        if (p.resident_b) {
+          const uint64_t b_desc0 = make_smem_desc(b_base_u + (uint32_t)(ks * TAPS) * B_TILE, 16, 1024, 2u);
+          if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < NM; ++j) {
-              const uint32_t aj = a_addr + tap_off + (uint32_t)j * 16u * sbo;
+            for (int tap = 0; tap < TAPS; ++tap) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              const uint32_t tap_off = (uint32_t)(((TAPS == 9 ? tap / 3 : 0)) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * 128u;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = make_smem_desc_bo(aj + k * 32, sbo, p.bo_mode);
-                const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, 2u);
-                umma_bf16(acc + j * BN, ad, bd, IDESC, (ks > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              for (int j = 0; j < NM; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = a_desc0 + (uint64_t)((tap_off + (uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
+                  const uint64_t bd = b_desc0 + (uint64_t)(((uint32_t)tap * B_TILE + (uint32_t)k * 32u) >> 4);
+                  umma_bf16(acc + j * BN, ad, bd, IDESC, (ks > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
               }
             }
-            if (!p.resident_b) {
-              umma_commit(&b_empty[sb]);
-              ++ib;
-            }
+            umma_commit(&a_empty[sa]);
           }
-          umma_commit(&a_empty[sa]);
-          ++ia;
+          __syncwarp();
+        } else {
+#pragma unroll 1
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const int sb = ib % SB;
+            mbar_wait(&b_full[sb], (ib / SB) & 1, 0x750 + sb);
+            tc_fence_after();
+            const uint32_t tap_off = (uint32_t)((TAPS == 9 ? tap / 3 : 0) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * 128u;
+            const uint64_t a_desc = a_desc0 + (uint64_t)(tap_off >> 4);
+            const uint64_t b_desc = make_smem_desc(b_base_u + (uint32_t)sb * B_TILE, 16, 1024, 2u);
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < NM; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = a_desc + (uint64_t)(((uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
+                  const uint64_t bd = b_desc + (uint64_t)(((uint32_t)k * 32u) >> 4);
+                  umma_bf16(acc + j * BN, ad, bd, IDESC, (ks > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+              umma_commit(&b_empty[sb]);
+              if (tap == TAPS - 1) umma_commit(&a_empty[sa]);
+            }
+            __syncwarp();
+            ++ib;
+          }
         }
-        umma_commit(&acc_full[buf]);
+        ++ia;
       }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global, overlapped with the next item's MMAs ----------------
@@ -221,11 +246,11 @@ size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
   return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + 1024;
 }
 
-template <int BN, int NM>
+template <int BN, int NM, int TAPS>
 int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
     configured = true;
   }
   static int num_sms = 0;
@@ -235,7 +260,7 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
     REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  haloconv_kernel<BN, NM><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
+  haloconv_kernel<BN, NM, TAPS><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -269,8 +294,11 @@ int haloconv_plan(HaloConvParams* p, int BN, int NM) {
 }
 
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream) {
-#define HINST(bn, nm) \
-  if (BN == bn && NM == nm) return launch_halo_inst<bn, nm>(p, stream);
+  REFID_REQUIRE((p.num_taps == 9 && p.halo == 1 && p.pitch_px == 10) || (p.num_taps == 1 && p.halo == 0 && p.pitch_px == 8),
+                "haloconv: taps/halo/pitch %d/%d/%d unsupported", p.num_taps, p.halo, p.pitch_px);
+#define HINST(bn, nm)                                                             \
+  if (BN == bn && NM == nm)                                                       \
+    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9>(p, stream) : launch_halo_inst<bn, nm, 1>(p, stream);
   HINST(32, 1) HINST(64, 1) HINST(128, 1) HINST(256, 1)
   HINST(32, 2) HINST(64, 2) HINST(128, 2)
 #undef HINST

@@ -32,7 +32,6 @@ struct HaloConvParams {
   int num_items;                  // tiles * n_blocks
   int resident_b;                 // weights stay in shared memory for the whole kernel (n_blocks == 1)
   int stages_a, stages_b;
-  int bo_mode;  // experiment switch: how the swizzle base offset of shifted A descriptors is formed
 };
 
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);

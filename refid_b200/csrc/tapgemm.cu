@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   uint64_t* acc_bar = empty_bar + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   const int tile = blockIdx.x;
@@ -151,16 +151,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   const int total_iters = total_slabs * p.num_taps;
 
   if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmB);
-      int it = 0;
-      int kglob = 0;
-      for (int src = 0; src < p.nsrc; ++src) {
-        for (int slab = 0; slab < p.src_slabs[src]; ++slab, kglob += BK) {
-          for (int tap = 0; tap < p.num_taps; ++tap, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + s);
+    // TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues.
+    if (elect_one()) tma_prefetch_desc(&p.tmB);
+    int it = 0;
+    int kglob = 0;
+    for (int src = 0; src < p.nsrc; ++src) {
+      for (int slab = 0; slab < p.src_slabs[src]; ++slab, kglob += BK) {
+        for (int tap = 0; tap < p.num_taps; ++tap, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + s);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
             uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
             uint8_t* b_dst = a_dst + A_BYTES;
@@ -172,23 +173,25 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        mbar_wait(&full_bar[s], ph, 0x200 + s);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
+    // MMA issuer: uniform loop, elected lane issues; descriptors are `stage base + constant`.
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_u = smem_u32(smem);
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(&full_bar[s], ph, 0x200 + s);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u + (uint32_t)s * STAGE_BYTES;
+      const uint64_t ad0 = make_smem_desc(a_addr, 16, SBO, SWZ);
+      const uint64_t bd0 = make_smem_desc(a_addr + A_BYTES, 16, SBO, SWZ);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, SBO, SWZ);
-          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, SBO, SWZ);
-          umma_bf16(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tm, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), IDESC, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[s]);
+        if (it == total_iters - 1) umma_commit(acc_bar);
       }
-      umma_commit(acc_bar);
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------

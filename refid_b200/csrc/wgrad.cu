@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   uint64_t* acc_bar = empty_bar + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int bpt = 128 / p.CB;  // channel blocks per M tile
   const int blocks_per_tap = p.src_blocks[0] + (p.nsrc > 1 ? p.src_blocks[1] : 0);
@@ -53,20 +53,21 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 
   if (my_tiles > 0 && my_mt > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int it = 0;
-        for (int pt = blockIdx.x; pt < p.num_tiles; pt += gridDim.x) {
-          const int tx_i = pt % p.tiles_x;
-          const int ty_i = (pt / p.tiles_x) % p.tiles_y;
-          const int tn_i = pt / (p.tiles_x * p.tiles_y);
-          const int x0 = tx_i * p.TW, y0 = ty_i * p.TH, n0 = tn_i * p.TN;
-          for (int mt = 0; mt < my_mt; ++mt, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1, 0x400 + s);
-            const int b0 = (mt0 + mt) * bpt;
-            int nvalid = total_blocks - b0;
-            if (nvalid > bpt) nvalid = bpt;
+      // TMA producer: uniform loop, one elected lane issues
+      int it = 0;
+      for (int pt = blockIdx.x; pt < p.num_tiles; pt += gridDim.x) {
+        const int tx_i = pt % p.tiles_x;
+        const int ty_i = (pt / p.tiles_x) % p.tiles_y;
+        const int tn_i = pt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx_i * p.TW, y0 = ty_i * p.TH, n0 = tn_i * p.TN;
+        for (int mt = 0; mt < my_mt; ++mt, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1, 0x400 + s);
+          const int b0 = (mt0 + mt) * bpt;
+          int nvalid = total_blocks - b0;
+          if (nvalid > bpt) nvalid = bpt;
+          if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nvalid * 128 * p.CB * 2 + Q_TILE_BYTES));
             uint8_t* p_dst = smem + (size_t)s * STAGE_BYTES;
             uint8_t* q_dst = p_dst + P_TILE_BYTES;
@@ -90,31 +91,36 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, p.BNq, 1, 1);
-        const uint32_t swzP = p.CB == 64 ? 2u : 4u, swzQ = p.CBq == 64 ? 2u : 4u;
-        const uint32_t lboP = 128u * p.CB * 2u, sboP = 8u * p.CB * 2u, kstepP = 16u * p.CB * 2u;
-        const uint32_t lboQ = 128u * p.CBq * 2u, sboQ = 8u * p.CBq * 2u, kstepQ = 16u * p.CBq * 2u;
-        int it = 0;
-        for (int t = 0; t < my_tiles; ++t) {
-          for (int mt = 0; mt < my_mt; ++mt, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            mbar_wait(&full_bar[s], ph, 0x500 + s);
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-            const uint32_t q_addr = p_addr + P_TILE_BYTES;
+      // MMA issuer: uniform loop, elected lane issues; per-MMA descriptors are `stage base + ks * step`
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = smem_u32(smem);
+      const uint32_t idesc = make_idesc_bf16(128, p.BNq, 1, 1);
+      const uint32_t swzP = p.CB == 64 ? 2u : 4u, swzQ = p.CBq == 64 ? 2u : 4u;
+      const uint32_t lboP = 128u * p.CB * 2u, sboP = 8u * p.CB * 2u;
+      const uint32_t lboQ = 128u * p.CBq * 2u, sboQ = 8u * p.CBq * 2u;
+      const uint64_t kstepP = (uint64_t)((16u * p.CB * 2u) >> 4), kstepQ = (uint64_t)((16u * p.CBq * 2u) >> 4);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int mt = 0; mt < my_mt; ++mt, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&full_bar[s], ph, 0x500 + s);
+          tc_fence_after();
+          const uint32_t p_addr = smem_u + (uint32_t)s * STAGE_BYTES;
+          const uint64_t ad0 = make_smem_desc(p_addr, lboP, sboP, swzP);
+          const uint64_t bd0 = make_smem_desc(p_addr + P_TILE_BYTES, lboQ, sboQ, swzQ);
+          const uint32_t d_addr = tm + (uint32_t)(mt * p.BNq);
+          if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t ad = make_smem_desc(p_addr + ks * kstepP, lboP, sboP, swzP);
-              const uint64_t bd = make_smem_desc(q_addr + ks * kstepQ, lboQ, sboQ, swzQ);
-              umma_bf16(tmem_base + (uint32_t)(mt * p.BNq), ad, bd, idesc, (t > 0 || ks > 0) ? 1u : 0u);
-            }
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16(d_addr, ad0 + ks * kstepP, bd0 + ks * kstepQ, idesc, (t > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&empty_bar[s]);
           }
+          __syncwarp();
         }
-        umma_commit(acc_bar);
       }
+      if (elect_one()) umma_commit(acc_bar);
+      __syncwarp();
     } else {
       const int q = warp & 3;
       const int m = q * 32 + lane;

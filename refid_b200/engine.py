@@ -40,6 +40,7 @@ def _bind(L):
     L.refid_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.refid_backward.argtypes = [c_void_p, c_void_p, c_void_p]
     L.refid_profile.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.refid_profile_csv.argtypes = [c_void_p, c_int, ctypes.c_char_p, c_void_p]
     L.refid_num_launches.argtypes = [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
     L.refid_debug_tensor.argtypes = [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p)] + [ctypes.POINTER(c_int)] * 5
     L._refid_bound = True
@@ -106,6 +107,9 @@ class Engine:
         _lib.check(self.L.refid_profile(self.h, int(with_backward), ms, fl, n, self._stream()), "refid_profile")
         names = ("conv_fwd", "conv_dgrad", "wgrad", "other")
         return {k: {"ms": ms[i], "flops": fl[i], "launches": n[i]} for i, k in enumerate(names)}
+
+    def profile_csv(self, path, with_backward=True):
+        _lib.check(self.L.refid_profile_csv(self.h, int(with_backward), str(path).encode(), self._stream()), "refid_profile_csv")
 
     def num_launches(self):
         a, b = c_int(0), c_int(0)

@@ -1,0 +1,55 @@
+// Microbenchmark: tcgen05.mma issue rate (cycles per K=16 MMA) for SS-mode bf16, per (M,N), operands in swizzle-128B smem.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu ; run on a B200.
+#include "../../refid_b200/csrc/common.cuh"
+#include "../../refid_b200/csrc/common.cu"
+using namespace refid;
+
+__global__ void __launch_bounds__(128, 1) k_rate(int M, int N, int iters, int a_stride, int b_stride, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async();
+  if (threadIdx.x < 32) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(M, N, 0, 0);
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + 96 * 1024;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      // 4 K-steps per "stage"; rotate over distinct smem regions so reads are real
+      const uint32_t aa = a0 + (uint32_t)((it & 3) * a_stride), bb = b0 + (uint32_t)((it & 3) * b_stride);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        umma_bf16(tm + (uint32_t)((it & 1) * N), make_smem_desc(aa + k * 32, 16, 1024, 2), make_smem_desc(bb + k * 32, 16, 1024, 2), idesc, 1);
+      }
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0, 1);
+    long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 148 * 8);
+  { cudaError_t e0 = cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); printf("attr: %s\n", cudaGetErrorString(e0)); }
+  int Ms[] = {128, 64}; int Ns[] = {32, 64, 96, 128, 192, 256};
+  for (int M : Ms) for (int N : Ns) {
+    const int iters = 2000;
+    k_rate<<<148, 128, 201 * 1024 + 1024>>>(M, N, iters, 16384, 16384, d);
+    cudaError_t e = cudaGetLastError(); cudaError_t e2 = cudaDeviceSynchronize(); if (e == cudaSuccess) e = e2;
+    long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    double cyc = (double)mx / (iters * 4);
+    double ideal = (M < 128 ? 128 : M) * (double)N / 256.0;
+    printf("M=%3d N=%3d: %.1f cyc/MMA (floor %.0f) eff %.2f  flop/clk/SM %.0f  %s\n", M, N, cyc, ideal, ideal * (M / 128.0) / cyc * (M<128?1:1),
+           2.0 * M * N * 16 / cyc, cudaGetErrorString(e));
+  }
+  return 0;
+}
