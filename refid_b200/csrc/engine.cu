@@ -9,7 +9,9 @@
 // Gradient convention: for an activation tensor X = act(Z) the gradient buffer holds dL/dZ ("GZ"): every consumer
 // multiplies its contribution by act'(.) (a linear mask) while accumulating, so the producer of X can feed the buffer
 // straight into its weight-gradient and data-gradient GEMMs.
+#include <algorithm>
 #include <functional>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -51,9 +53,20 @@ struct Ten {
   bool gwritten = false;
   int parent = -1;
   long rel = 0;              // byte offset relative to the parent (views)
+  int series = -1, slot = -1;  // time series this tensor is one slot of (contiguous over the T steps)
   std::vector<Pend> pending;  // gradient buffers still to be added (residual / skip-sum passthrough)
   bool contiguous() const { return pitch == C; }
   long elems() const { return (long)N * H * W * C; }
+};
+
+// A per-step tensor role (e.g. "the trunk's v at level 1, forward sweep") stored for all T steps in ONE contiguous array
+// of T+1 slots, slot = time step (+1 in the forward sweep; the spare slot is the zero initial state of recurrent
+// series).  Contiguity is what lets the weight gradient of a site be ONE GEMM over all T*B images at the end of the
+// backward pass instead of T small ones (the same weights are applied at every step).
+struct Series {
+  long base = -1;       // byte offset of slot 0 in the workspace
+  size_t slot_bytes = 0;
+  long gbase = -1;      // persistent gradient (dL/dZ) array, allocated when the producing site's wgrad is batched
 };
 
 struct GBuf {
@@ -117,6 +130,13 @@ struct Engine {
   std::vector<std::function<int()>> tape;
   std::vector<std::pair<size_t, size_t>> f32_zero;
   std::vector<int> release_after;  // pool buffers of pending addends consumed by the launch being built
+  std::vector<Series> series;
+  std::map<std::string, int> series_idx;
+  int cur_slot = -1;       // slot of the per-step tensors being created (-1: outside the time sweeps)
+  int step_seq = 0;        // running index of new_tensor calls inside the current step (= the tensor's role)
+  std::string cur_sdir;    // "b" / "f": sweep the current step belongs to
+  std::vector<std::vector<ConvOp>> site_calls;  // forward conv calls per site (plan time)
+  std::vector<char> site_batched;               // weight/bias gradient of this site is one batched launch
 
   // per-call io
   const float* io_x = nullptr;
@@ -270,7 +290,47 @@ struct Engine {
     return (long)off;
   }
 
+  int new_series(size_t slot_bytes) {
+    Series sr;
+    sr.slot_bytes = slot_bytes;
+    sr.base = act_alloc(slot_bytes * (size_t)(T + 1));
+    series.push_back(sr);
+    return (int)series.size() - 1;
+  }
+
+  int series_tensor(int sidx, int slot, int N, int Hh, int Ww, int C, const std::string& name = "") {
+    Ten t;
+    t.N = N;
+    t.H = Hh;
+    t.W = Ww;
+    t.C = C;
+    t.pitch = C;
+    t.series = sidx;
+    t.slot = slot;
+    t.off = series[sidx].base + (long)slot * (long)series[sidx].slot_bytes;
+    tens.push_back(t);
+    if (!name.empty()) named[name] = (int)tens.size() - 1;
+    return (int)tens.size() - 1;
+  }
+
   int new_tensor(int N, int Hh, int Ww, int C, const std::string& name = "") {
+    if (cur_slot >= 0) {  // inside a time step: the tensor is one slot of its role's series
+      const std::string key = cur_sdir + "#" + std::to_string(step_seq++);
+      const size_t bytes = (size_t)N * Hh * Ww * C * 2;
+      auto it = series_idx.find(key);
+      int sidx;
+      if (it == series_idx.end()) {
+        sidx = new_series(bytes);
+        series_idx[key] = sidx;
+      } else {
+        sidx = it->second;
+        if (series[sidx].slot_bytes != bytes) {
+          set_error("series %s: slot size changed between steps", key.c_str());
+          return -1;
+        }
+      }
+      return series_tensor(sidx, cur_slot, N, Hh, Ww, C, name);
+    }
     Ten t;
     t.N = N;
     t.H = Hh;
@@ -337,6 +397,12 @@ struct Engine {
       tens[p].gwritten = true;  // children fill the parent's buffer piecewise (each element exactly once)
       tens[id].gidx = tens[p].gidx;
       tens[id].goff = tens[p].goff + tens[id].rel;
+      return;
+    }
+    if (tens[id].series >= 0 && series[tens[id].series].gbase >= 0) {  // persistent per-step gradient array
+      const Series& sr = series[tens[id].series];
+      tens[id].gidx = -1;
+      tens[id].goff = sr.gbase + (long)tens[id].slot * (long)sr.slot_bytes;
       return;
     }
     tens[id].gidx = galloc((size_t)tens[id].elems() * 2);
@@ -453,7 +519,7 @@ struct Engine {
       emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, "addmask");
       return 0;
     }
-    gbufs[src_gidx].refs++;
+    if (src_gidx >= 0) gbufs[src_gidx].refs++;
     tens[id].pending.push_back(Pend{src_gidx, src_off});
     return 0;
   }
@@ -524,6 +590,7 @@ struct Engine {
       if (op.act == ACT_LRELU) tens[op.out].mask_off = tens[op.out].off;
       if (op.act == ACT_GELU) tens[op.out].mask_off = act_alloc((size_t)tens[op.out].elems() * 2);
     }
+    else if (op.out >= 0 && !name.empty()) named[name] = op.out;
     if (op.post >= 0 && op.out2 < 0) op.out2 = new_tensor(in0.N, oh, ow, cout, name.empty() ? "" : name + "+");
     if (!dry) {
       cur_label = s.key;
@@ -589,6 +656,8 @@ struct Engine {
     if (train && !op.no_tape) {
       Engine* self = this;
       tape.push_back([self, op]() { return self->conv_bwd(op); });
+      if (site_calls.size() < sites.size()) site_calls.resize(sites.size());
+      site_calls[op.site].push_back(op);
     }
     return op.out2 >= 0 && op.out < 0 ? op.out2 : op.out;
   }
@@ -614,20 +683,25 @@ struct Engine {
     }
     const __nv_bfloat16* gz = nullptr;
     if (finalize(op.out, &gz)) return 1;
-    if (!gz) return 0;
+    if (!gz) {
+      REFID_REQUIRE(!(op.site < (int)site_batched.size() && site_batched[op.site]),
+                    "no gradient reaches one step of batched site %s", s.key.c_str());
+      return 0;
+    }
     cur_label = s.key;
     const Ten o = tens[op.out];
     const Ten in0 = tens[op.in[0]];
     const int cout = o.C;
     int cin_total = 0;
     for (int k = 0; k < op.nin; ++k) cin_total += tens[op.in[k]].C;
+    const bool batched = op.site < (int)site_batched.size() && site_batched[op.site];
     // bias gradient
-    if (s.b_off >= 0) {
+    if (s.b_off >= 0 && !batched) {
       REFID_REQUIRE(o.contiguous(), "bias gradient on a strided tensor (%s)", s.key.c_str());
       emit_colsum(gz, (long)o.N * o.H * o.W, cout, gflat + s.b_off);
     }
-    // weight gradient
-    if (!dry) {
+    // weight gradient (per call; batched sites get one launch over all steps at the end of the backward plan)
+    if (!dry && !batched) {
       ConvDesc d;
       memset(&d, 0, sizeof(d));
       ActSrc q;
@@ -915,7 +989,8 @@ struct Engine {
     return id;
   }
 
-  int trunk(const std::string& p, int u, int hprev, const std::string& nm, int post, int out2_preset, int* out2) {
+  int trunk(const std::string& p, int u, int hprev, const std::string& nm, int post, int out2_preset, int* out2,
+            int h_preset = -1) {
     ConvOp a;
     a.site = site(p + ".main.0");
     a.in[0] = u;
@@ -938,6 +1013,7 @@ struct Engine {
     c.res = v;
     c.post = post;
     c.out2 = out2_preset;
+    c.out = h_preset;
     const int h = conv(c, nm + ".h");
     if (h < 0) return -1;
     if (out2) *out2 = post >= 0 ? (out2_preset >= 0 ? out2_preset : (int)tens.size() - 1) : -1;
@@ -1037,9 +1113,20 @@ struct Engine {
     }
     const char* dirs[2] = {"encoders_backward", "encoders_forward"};
     // ---- backward sweep t = T-1 .. 0 (XXNet_final_attenfusion_arch.py:172-181)
-    int hb[3];
-    for (int l = 0; l < 3; ++l) hb[l] = zero_tensor(B, H >> l, W >> l, (2 * b) << l, &zero_fwd);
+    // Recurrent states live in (T+1)-slot series: slot t = h_t, the spare slot is the zero initial state.
+    auto state_series = [&](int Hh, int Ww, int C, int pad_slot, int* pad_tensor) {
+      const int sidx = new_series((size_t)B * Hh * Ww * C * 2);
+      *pad_tensor = series_tensor(sidx, pad_slot, B, Hh, Ww, C);
+      tens[*pad_tensor].need_grad = false;
+      zero_fwd.push_back({(size_t)tens[*pad_tensor].off, (size_t)tens[*pad_tensor].elems() * 2});
+      return sidx;
+    };
+    int hb[3], hb_series[3];
+    for (int l = 0; l < 3; ++l) hb_series[l] = state_series(H >> l, W >> l, (2 * b) << l, T, &hb[l]);
     for (int t = T - 1; t >= 0; --t) {
+      cur_slot = t;
+      cur_sdir = "b";
+      step_seq = 0;
       int curx = -1;
       for (int l = 0; l < 3; ++l) {
         const std::string p = std::string(dirs[0]) + "." + std::to_string(l);
@@ -1058,7 +1145,8 @@ struct Engine {
           u = conv(ci, nm + ".u");
         }
         if (u < 0) return 1;
-        const int h = trunk(p + ".recurrent_block.forward_trunk", u, hb[l], nm, -1, -1, nullptr);
+        const int h = trunk(p + ".recurrent_block.forward_trunk", u, hb[l], nm, -1, -1, nullptr,
+                            series_tensor(hb_series[l], t, B, H >> l, W >> l, (2 * b) << l));
         if (h < 0) return 1;
         hb[l] = h;
         if (l < 2) {
@@ -1073,14 +1161,18 @@ struct Engine {
         }
       }
     }
+    cur_slot = -1;
     // Only the FINAL backward state reaches the forward sweep (list aliasing at :181).
     for (int l = 0; l < 3; ++l) mark_f32acc(hb[l]);
     // ---- forward sweep t = 0 .. T-1 (:185-216)
-    int hf[3], sd[3];
-    for (int l = 0; l < 3; ++l) hf[l] = zero_tensor(B, H >> l, W >> l, (2 * b) << l, &zero_fwd);
-    for (int i = 0; i < 3; ++i) sd[i] = zero_tensor(B, H >> (2 - i), W >> (2 - i), (4 * b) >> i, &zero_fwd);
+    int hf[3], sd[3], hf_series[3], sd_series[3];
+    for (int l = 0; l < 3; ++l) hf_series[l] = state_series(H >> l, W >> l, (2 * b) << l, 0, &hf[l]);
+    for (int i = 0; i < 3; ++i) sd_series[i] = state_series(H >> (2 - i), W >> (2 - i), (4 * b) >> i, 0, &sd[i]);
     const int sp_all = new_tensor(T * B, H, W, b, "sp_all");
     for (int t = 0; t < T; ++t) {
+      cur_slot = t + 1;
+      cur_sdir = "f";
+      step_seq = 0;
       int curx = -1;
       int dn[3];
       for (int l = 0; l < 3; ++l) {
@@ -1100,7 +1192,8 @@ struct Engine {
           u = conv(ci, nm + ".u");
         }
         if (u < 0) return 1;
-        const int h = trunk(p + ".recurrent_block.forward_trunk", u, hf[l], nm, -1, -1, nullptr);
+        const int h = trunk(p + ".recurrent_block.forward_trunk", u, hf[l], nm, -1, -1, nullptr,
+                            series_tensor(hf_series[l], t + 1, B, H >> l, W >> l, (2 * b) << l));
         if (h < 0) return 1;
         hf[l] = h;
         ConvOp cf;
@@ -1161,7 +1254,8 @@ struct Engine {
           post = head;
           preset = view(sp_all, t * B, B, 0, b);
         }
-        const int s = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2);
+        const int s = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2,
+                            series_tensor(sd_series[i], t + 1, B, H >> (2 - i), W >> (2 - i), (4 * b) >> i));
         if (s < 0) return 1;
         sd[i] = s;
         xin = o2;
@@ -1176,6 +1270,7 @@ struct Engine {
       cp.nchw_nstride = (long)T * cfg.out_chn * H * W;
       conv(cp);
     }
+    cur_slot = -1;
     // pred backward is batched over all T steps: gout -> bf16 NHWC (padded to 32 channels), wgrad + dgrad once
     if (train) {
       const int ps = site("pred");
@@ -1216,6 +1311,91 @@ struct Engine {
       fwd.insert(fwd.begin(), pre.begin(), pre.end());
       fwd_meta.insert(fwd_meta.begin(), pre.size(), LaunchMeta{LC_OTHER, 0.0, "memset:state0"});
     }
+    decide_batching();
+    return 0;
+  }
+
+  // A site called once per time step with contiguous per-step operands gets ONE weight/bias-gradient launch over all
+  // T*B images; its per-step output gradients are then kept in a persistent series array instead of the pool.
+  void decide_batching() {
+    site_batched.assign(sites.size(), 0);
+    site_calls.resize(sites.size());
+    if (!train) return;
+    static const bool disabled = getenv("REFID_NO_BATCHED_WGRAD") != nullptr;
+    if (disabled) return;
+    for (size_t si = 0; si < sites.size(); ++si) {
+      auto& calls = site_calls[si];
+      if (calls.size() < 2) continue;
+      bool ok = true;
+      for (auto& c : calls)
+        if (c.out < 0 || c.nchw_out || tens[c.out].series < 0 || tens[c.out].parent >= 0) ok = false;
+      if (!ok) continue;
+      std::sort(calls.begin(), calls.end(), [&](const ConvOp& a, const ConvOp& b2) { return tens[a.out].slot < tens[b2.out].slot; });
+      const Ten o0 = tens[calls[0].out];
+      for (size_t i = 0; i < calls.size() && ok; ++i) {
+        const Ten& o = tens[calls[i].out];
+        if (o.series != o0.series || o.slot != o0.slot + (int)i || calls[i].nin != calls[0].nin ||
+            calls[i].kind != calls[0].kind || !o.contiguous())
+          ok = false;
+        for (int k = 0; k < calls[0].nin && ok; ++k) {
+          const Ten& a0 = tens[calls[0].in[k]];
+          const Ten& a = tens[calls[i].in[k]];
+          const long stride = (long)a0.N * a0.H * a0.W * a0.pitch * 2;
+          if (a.C != a0.C || a.pitch != a0.pitch || a.N != a0.N || a.H != a0.H || a.W != a0.W ||
+              a.off != a0.off + (long)i * stride)
+            ok = false;
+        }
+      }
+      if (!ok) continue;
+      site_batched[si] = 1;
+      Series& sr = series[o0.series];
+      if (sr.gbase < 0) sr.gbase = act_alloc(sr.slot_bytes * (size_t)(T + 1));
+    }
+  }
+
+  // Emitted after the whole tape: one bias column-sum and one weight-gradient GEMM per batched site.
+  int emit_batched_grads() {
+    for (size_t si = 0; si < sites.size(); ++si) {
+      if (!site_batched[si]) continue;
+      const Site& s = sites[si];
+      const auto& calls = site_calls[si];
+      const ConvOp& op = calls[0];
+      const int n = (int)calls.size();
+      const Ten o = tens[op.out];
+      const Ten in0 = tens[op.in[0]];
+      const Series& sr = series[o.series];
+      const __nv_bfloat16* gz = P(sr.gbase + (long)o.slot * (long)sr.slot_bytes);
+      cur_label = s.key;
+      if (s.b_off >= 0) emit_colsum(gz, (long)n * o.N * o.H * o.W, o.C, gflat + s.b_off);
+      if (dry) continue;
+      ConvDesc d;
+      memset(&d, 0, sizeof(d));
+      ActSrc q;
+      if (op.kind == CK_UP2) {
+        d.kind = CK_UP2_DGRAD;
+        d.src[0] = {gz, o.C, o.pitch};
+        d.nsrc = 1;
+        d.N = n * o.N;
+        d.H = o.H;
+        d.W = o.W;
+        q = {P(in0.off), in0.C, in0.pitch};
+      } else {
+        d.kind = op.kind;
+        d.nsrc = op.nin;
+        for (int k = 0; k < op.nin; ++k) {
+          const Ten& t = tens[op.in[k]];
+          d.src[k] = {P(t.off), t.C, t.pitch};
+        }
+        d.N = n * in0.N;
+        d.H = in0.H;
+        d.W = in0.W;
+        q = {gz, o.C, o.pitch};
+      }
+      WgradLaunch wl;
+      if (build_wgrad(d, q, gflat + s.w_off, &wl)) return 1;
+      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, conv_flops(op) * n, ":wgrad");
+    }
+    cur_label = "";
     return 0;
   }
 
@@ -1244,6 +1424,11 @@ struct Engine {
     tape.clear();
     f32_zero.clear();
     release_after.clear();
+    series.clear();
+    series_idx.clear();
+    site_calls.clear();
+    site_batched.clear();
+    cur_slot = -1;
     act_top = gtop = 0;
     planned = false;
     cur = &fwd;
@@ -1261,6 +1446,7 @@ struct Engine {
       }
       for (int i = (int)tape.size() - 1; i >= 0; --i)
         if (tape[i]()) return 1;
+      if (emit_batched_grads()) return 1;
     }
     tape.clear();
     planned = !dry;
