@@ -1,0 +1,79 @@
+"""The two callers of the hot path, mirrored from the reference's model wrapper so the parity tests read like its usage:
+
+  * `optimize_parameters`  -- basicsr/models/twoImage_event_recurrent_model.py:273-310: zero_grad, `net_g(x=lq,
+    event=voxel)`, Charbonnier loss (losses.py:28-30, eps 1e-12, mean), the `+ 0 * sum(p.sum())` term that gives the
+    never-used parameters a zero gradient (:301), backward, `clip_grad_norm_(..., 0.01)` unless `use_grad_clip: false`
+    (:304-306), optimizer step (AdamW / Adam from `train.optim_g`, :67-95);
+  * `test` -- :312-330: eval + no_grad, `val.max_minibatch` chunking, outputs concatenated on dim 0.
+
+Data loading, validation bookkeeping, logging, checkpoints and schedulers stay with the reference (out of scope,
+SURVEY.md 8); `feed_data` only moves the three tensors to the device (:97-104).
+"""
+from copy import deepcopy
+
+import torch
+
+from .plugin import define_network
+
+
+def charbonnier(pred, target, eps=1e-12):
+    return torch.sqrt((pred - target) ** 2 + eps).mean()
+
+
+class TwoImageEventRecurrentRestorationModel:
+    def __init__(self, opt, device="cuda"):
+        self.opt = opt
+        self.device = torch.device(device)
+        self.net_g = define_network(deepcopy(opt["network_g"])).to(self.device)
+        self.is_train = "train" in opt
+        self.optimizer_g = None
+        if self.is_train:
+            self.net_g.train()
+            train_opt = deepcopy(opt["train"])
+            pix = train_opt.get("pixel_opt") or {"type": "CharbonnierLoss"}
+            if pix.get("type", "CharbonnierLoss") != "CharbonnierLoss":
+                raise NotImplementedError("only CharbonnierLoss is used by the shipped option files")
+            self.loss_weight = float(pix.get("loss_weight", 1.0))
+            og = train_opt.get("optim_g", {"type": "AdamW", "lr": 2e-4, "weight_decay": 1e-4, "betas": [0.9, 0.99]})
+            og = dict(og)
+            optim_type = og.pop("type")
+            params = [p for p in self.net_g.parameters() if p.requires_grad]
+            if optim_type == "AdamW":
+                self.optimizer_g = torch.optim.AdamW(params, **og)
+            elif optim_type == "Adam":
+                self.optimizer_g = torch.optim.Adam(params, **og)
+            else:
+                raise NotImplementedError(f"optimizer {optim_type} is not supperted yet.")
+        self.log_dict = {}
+
+    def feed_data(self, data):
+        self.lq = data["lq"].to(self.device)
+        self.voxel = data["voxel"].to(self.device)
+        if "gt" in data:
+            self.gt = data["gt"].to(self.device)
+
+    def optimize_parameters(self, current_iter=0):
+        self.optimizer_g.zero_grad()
+        pred = self.net_g(x=self.lq, event=self.voxel)
+        l_pix = self.loss_weight * charbonnier(pred, self.gt)
+        l_total = l_pix + 0 * sum(p.sum() for p in self.net_g.parameters())
+        l_total.backward()
+        if self.opt["train"].get("use_grad_clip", True):
+            torch.nn.utils.clip_grad_norm_(self.net_g.parameters(), 0.01)
+        self.optimizer_g.step()
+        self.log_dict = {"l_pix": l_pix.detach()}
+        return l_pix.detach()
+
+    def test(self):
+        self.net_g.eval()
+        with torch.no_grad():
+            n = self.lq.size(0)
+            m = (self.opt.get("val") or {}).get("max_minibatch", n)
+            outs, i = [], 0
+            while i < n:
+                j = min(i + m, n)
+                outs.append(self.net_g(x=self.lq[i:j], event=self.voxel[i:j]))
+                i = j
+            self.output = torch.cat(outs, dim=0)
+        self.net_g.train()
+        return self.output

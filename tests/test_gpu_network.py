@@ -122,3 +122,46 @@ def test_no_cpu_path():
     net = FinalBidirectionAttenfusion(img_chn=6, ev_chn=2, num_encoders=3, base_num_channels=32, num_block=1)
     with pytest.raises(RuntimeError):
         net(x=torch.rand(1, 6, 32, 32), event=torch.rand(1, 2, 2, 32, 32))
+
+
+def test_optimize_parameters_and_test_callers_match_oracle():
+    """The two callers of the path (reference twoImage_event_recurrent_model.py:273-330) through the option-file ->
+    define_network boundary: the loss of one optimize_parameters step equals the oracle's, the AdamW update (after
+    the 0.01 global-norm clip) points the same way element-wise, never-used parameters only see weight decay, and
+    test() with max_minibatch chunking equals an un-chunked forward."""
+    from oracle import refid_oracle as O
+    from refid_b200 import recurrent_model
+    B, T, H, W, ic, ec = 2, 2, 32, 32, 6, 2
+    opt = {"network_g": {"type": "FinalBidirectionAttenfusion", "img_chn": ic, "ev_chn": ec, "num_encoders": 3,
+                         "base_num_channels": 32, "num_block": 1, "num_residual_blocks": 2},
+           "train": {"optim_g": {"type": "AdamW", "lr": 2e-4, "weight_decay": 1e-4, "betas": [0.9, 0.99]}},
+           "val": {"max_minibatch": 1}}
+    P = paramgen.make_params(O.param_shapes(ic, ec), seed=0)
+    x, ev, gt = paramgen.make_inputs(B, T, H, W, ic, ec)
+    m = recurrent_model.TwoImageEventRecurrentRestorationModel(opt, device="cuda")
+    m.net_g.load_state_dict(P, strict=True)
+    m.feed_data({"lq": x, "voxel": ev, "gt": gt})
+    full = m.net_g(x=m.lq, event=m.voxel).detach()
+    assert torch.equal(m.test(), full)  # chunks of 1 sample == whole batch (no cross-sample coupling, SURVEY.md 8e)
+    l_pix = m.optimize_parameters(1)
+    _no_abort()
+    # oracle: same step on CPU
+    Q = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    loss = O.charbonnier(O.forward(Q, x, ev), gt) + 0 * sum(p.sum() for p in Q.values())
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(list(Q.values()), 0.01)
+    optim = torch.optim.AdamW(list(Q.values()), lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.99))
+    optim.step()
+    assert abs(l_pix.item() - loss.item()) < 2e-3
+    dead = set(O.dead_params(O.param_shapes(ic, ec)))
+    agree, total = 0.0, 0
+    for n, p in m.net_g.named_parameters():
+        d_mine = (p.detach().cpu() - P[n]).double()
+        d_ref = (Q[n].detach() - P[n]).double()
+        if n in dead:  # zero gradient => pure weight decay, identical on both sides
+            assert torch.allclose(d_mine, d_ref, atol=1e-9), n
+            continue
+        if p.numel() >= 1024:
+            agree += (torch.sign(d_mine) == torch.sign(d_ref)).double().sum().item()
+            total += p.numel()
+    assert agree / total > 0.9, agree / total
