@@ -114,6 +114,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / 64;
   h.n_blocks = total / BN;
   h.epi_seg = seg;
+  h.epi_shift = 0;
+  while ((1 << h.epi_shift) < seg) ++h.epi_shift;
   h.N = d.N;
   h.H = d.H;
   h.W = d.W;

@@ -8,8 +8,142 @@ namespace refid {
 
 namespace {
 
-constexpr int kHaloThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
+constexpr int kHaloThreads = 320;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-9: epilogue (two per TMEM lane quarter)
 constexpr int kHaloMaxStages = 8;
+
+// ---- epilogue with register prefetch --------------------------------------------------------------------------------
+// The epilogue's global reads (residuals, pending gradient addends, activation masks, skip-sum operands) do not depend
+// on the accumulator, so they are issued one 32-channel group AHEAD of use -- the first group of a tile before the
+// accumulator-ready wait -- instead of load -> ~800-cycle stall -> use in every 16-channel step.
+struct EpiPF {
+  uint4 a[4], b[4], c[4];  // pre, pre2, (sv | post): 32 channels of this thread's pixel each
+};
+
+__device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, bool valid, EpiPF& f) {
+  if (!valid) return;
+  if (e.pre) {
+    const uint4* q = reinterpret_cast<const uint4*>(e.pre + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f.a[i] = q[i];
+  }
+  if (e.pre2) {
+    const uint4* q = reinterpret_cast<const uint4*>(e.pre2 + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f.b[i] = q[i];
+  }
+  const __nv_bfloat16* third = e.sv ? e.sv : e.post;
+  if (third) {
+    const uint4* q = reinterpret_cast<const uint4*>(third + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f.c[i] = q[i];
+  }
+}
+
+__device__ __forceinline__ void unpack16(const uint4* q, float* f) {
+  const uint32_t w[8] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[2 * i] = bf16_lo(w[i]);
+    f[2 * i + 1] = bf16_hi(w[i]);
+  }
+}
+
+__device__ __forceinline__ void unpack32(const uint4* q, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[8 * i + 0] = bf16_lo(q[i].x); f[8 * i + 1] = bf16_hi(q[i].x);
+    f[8 * i + 2] = bf16_lo(q[i].y); f[8 * i + 3] = bf16_hi(q[i].y);
+    f[8 * i + 4] = bf16_lo(q[i].z); f[8 * i + 5] = bf16_hi(q[i].z);
+    f[8 * i + 6] = bf16_lo(q[i].w); f[8 * i + 7] = bf16_hi(q[i].w);
+  }
+}
+__device__ __forceinline__ void store32(__nv_bfloat16* ptr, const float* v) {
+  uint4* o = reinterpret_cast<uint4*>(ptr);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t;
+    t.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    t.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    o[i] = t;
+  }
+}
+
+// Epilogue of 32 consecutive output channels of one pixel (same arithmetic as epi_apply16 in tapgemm.cu; see EpiDesc),
+// global operands taken from the prefetched registers.  `off` = element offset of channel 0 of the group.
+__device__ __forceinline__ void epi_apply32_pf(const EpiDesc& e, float* v, size_t off, int cseg, int n, int y, int x,
+                                               const EpiPF& f) {
+  if (e.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + e.coff + cseg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(b4 + i);
+      v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+  if (e.pre) {
+    float t[32];
+    unpack32(f.a, t);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += t[i];
+  }
+  if (e.pre2) {
+    float t[32];
+    unpack32(f.b, t);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += t[i];
+  }
+  if (e.sv) {
+    float t[32];
+    unpack32(f.c, t);
+    if (e.act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(t[i]);
+    } else {
+      const float sl = e.slope;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= (t[i] > 0.f ? 1.f : sl);
+    }
+  } else {
+    if (e.out_pre) store32(e.out_pre + off, v);
+    if (e.act == ACT_LRELU) {
+      const float sl = e.slope;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+    } else if (e.act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+    }
+  }
+  if (e.out) store32(e.out + off, v);
+  if (e.out_nchw && cseg == 0) {
+    float* o = e.out_nchw + (size_t)n * e.nchw_nstride + (size_t)y * e.OW + (size_t)x;
+    const size_t plane = (size_t)e.OH * e.OW;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < e.nchw_C) o[i * plane] = v[i];
+  }
+  if (e.out_f32) {
+    float4* o = reinterpret_cast<float4*>(e.out_f32 + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = o[i];
+      t.x += v[4 * i];
+      t.y += v[4 * i + 1];
+      t.z += v[4 * i + 2];
+      t.w += v[4 * i + 3];
+      o[i] = t;
+    }
+  }
+  if (e.out2) {
+    float t[32];
+    unpack32(f.c, t);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] += v[i];
+    store32(e.out2 + off, t);
+  }
+}
 
 // Shifted taps: a tap (dy,dx) only moves the START ADDRESS of the A descriptor by whole 128-byte pixel rows inside the halo
 // patch.  The 128B swizzle XOR is a function of the absolute shared-memory address bits on both the TMA write and the UMMA
@@ -62,7 +196,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], 8);
     }
     mbar_init(wres_bar, 1);
     fence_barrier_init();
@@ -192,9 +326,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global, overlapped with the next item's MMAs ----------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // Eight warps: warp w may only touch TMEM lanes 32*(w%4)..+31, so two warps share a lane quarter and split the
+    // item's 32-channel groups (even / odd).  One warp per scheduler cannot hide its own ALU/LSU latency.
+    const int q = warp & 3;            // TMEM lane quarter
+    const int hsel = (warp - 2) >> 2;  // which half of the groups
     const int m = q * 32 + lane;
     const int ty = m >> 3, tx = m & 7;
+    constexpr int GPT = BN / 32;  // groups per pixel tile
+    constexpr int G = NM * GPT;
+    const int epi_mask = p.epi_seg - 1;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
@@ -202,25 +342,46 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
       const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
       const int n = tile / tiles_per_img;
       const uint32_t buf = it & 1;
+      auto group_ctx = [&](int g, const EpiDesc*& e, size_t& off, int& cseg, int& y, bool& valid) {
+        const int j = g / GPT, c0 = (g % GPT) * 32;
+        y = y0 + j * 16 + ty;
+        valid = (y < p.H) && (x < p.W);
+        const int ch = nblk * BN + c0;
+        e = &p.epi[ch >> p.epi_shift];
+        cseg = ch & epi_mask;
+        const size_t pix = ((size_t)n * e->OH + (size_t)y) * e->OW + (size_t)x;
+        off = pix * (size_t)e->C + e->coff + cseg;
+      };
+      EpiPF cur, nxt;
+      if (hsel < G) {
+        const EpiDesc* e;
+        size_t off;
+        int cseg, y;
+        bool valid;
+        group_ctx(hsel, e, off, cseg, y, valid);
+        epi_prefetch32(*e, off, valid, cur);
+      }
       mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < NM; ++j) {
-        const int y = y0 + j * 16 + ty;
-        const bool valid = (y < p.H) && (x < p.W);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c0), v);
-          tmem_ld_wait();
-          if (valid) {
-            const int ch = nblk * BN + c0;
-            const EpiDesc& e = p.epi[ch / p.epi_seg];
-            const size_t pix = ((size_t)n * e.OH + (size_t)y) * e.OW + (size_t)x;
-            const size_t base = pix * (size_t)e.C + e.coff;
-            epi_apply16(e, v, e.bias, base, ch % p.epi_seg, n, y, x);
-          }
+      for (int g = hsel; g < G; g += 2) {
+        const EpiDesc* e;
+        size_t off;
+        int cseg, y;
+        bool valid;
+        if (g + 2 < G) {
+          group_ctx(g + 2, e, off, cseg, y, valid);
+          epi_prefetch32(*e, off, valid, nxt);
         }
+        group_ctx(g, e, off, cseg, y, valid);
+        const int j = g / GPT, c0 = (g % GPT) * 32;
+        float v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c0);
+        tmem_ld16(taddr, v);
+        tmem_ld16(taddr + 16, v + 16);
+        tmem_ld_wait();
+        if (valid) epi_apply32_pf(*e, v, off, cseg, n, y, x, cur);
+        cur = nxt;
       }
       tc_fence_before();
       __syncwarp();

@@ -20,7 +20,8 @@ struct HaloConvParams {
   CUtensorMap tmA[2];  // per source: dims (C, W, H, N), box (64, pitch_px, patch_rows, 1), 128B swizzle
   CUtensorMap tmB;     // packed weights [rows][K], box (64, BN)
   EpiDesc epi[kMaxNBlocks];
-  int epi_seg;      // output channels per EpiDesc (divides BN)
+  int epi_seg;      // output channels per EpiDesc (power of two, divides BN)
+  int epi_shift;    // log2(epi_seg)
   int num_taps;     // 9 or 1
   int halo;         // 1 (3x3) or 0 (1x1)
   int pitch_px;     // pixels per patch row in shared memory (multiple of 8)

@@ -142,7 +142,9 @@ def test_optimize_parameters_and_test_callers_match_oracle():
     m.net_g.load_state_dict(P, strict=True)
     m.feed_data({"lq": x, "voxel": ev, "gt": gt})
     full = m.net_g(x=m.lq, event=m.voxel).detach()
-    assert torch.equal(m.test(), full)  # chunks of 1 sample == whole batch (no cross-sample coupling)
+    # chunks of 1 sample == whole batch (no cross-sample coupling); not bit-equal: EGACA's global pool is
+    # accumulated with fp32 atomics whose order depends on the launch geometry
+    assert (m.test() - full).abs().max().item() < 2e-3
     l_pix = m.optimize_parameters(1)
     _no_abort()
     # oracle: same step on CPU
