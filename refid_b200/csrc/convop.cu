@@ -245,9 +245,62 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
   return 0;
 }
 
+// Returns 1 when lowered onto the halo-wgrad kernel, 0 when the op does not qualify, -1 on error.
+static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
+  if (d.kind != CK_3X3) return 0;
+  static const int disabled = getenv("REFID_NO_HALO_WGRAD") ? 1 : 0;
+  if (disabled) return 0;
+  int mode = 0;
+  if (q.C == 64) mode = 64;
+  else if (q.C % 128 == 0) mode = 128;
+  if (!mode) return 0;
+  int cp_total = 0;
+  for (int s = 0; s < d.nsrc; ++s) {
+    if (d.src[s].C % mode) return 0;
+    cp_total += d.src[s].C;
+  }
+  HaloWgradParams& h = l->hp;
+  memset(&h, 0, sizeof(h));
+  h.mode = mode;
+  h.out = outp;
+  h.CQ = q.C;
+  h.cp_total = cp_total;
+  h.nsrc = d.nsrc;
+  for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / 64;
+  h.total_slabs = cp_total / 64;
+  h.N = d.N;
+  h.H = d.H;
+  h.W = d.W;
+  h.tiles_x = (d.W + 7) / 8;
+  h.tiles_y = (d.H + 15) / 16;
+  h.num_tiles = h.tiles_x * h.tiles_y * d.N;
+  h.jobs = mode == 64 ? h.total_slabs : (h.total_slabs / 2) * 3 * (q.C / 128);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      num_sms = 148;
+  }
+  h.chunks = num_sms / h.jobs;
+  if (h.chunks < 1) h.chunks = 1;
+  if (h.chunks > h.num_tiles) h.chunks = h.num_tiles;
+  const int rows = mode == 64 ? 18 : 16;
+  for (int s = 0; s < d.nsrc; ++s)
+    if (make_act_map(&h.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, 64, 10, rows, 1)) return -1;
+  if (make_act_map(&h.tmQ, q.ptr, d.N, d.H, d.W, q.pitch, q.C, 0, 0, 1, 64, 8, 16, 1)) return -1;
+  l->use_halo = 1;
+  return 1;
+}
+
 int build_wgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
   TapTable tt;
   if (fill_taps(d.kind, d.parity, &tt)) return 1;
+  l->use_halo = 0;
+  {
+    const int r = try_build_halowgrad(d, q, outp, l);
+    if (r < 0) return 1;
+    if (r > 0) return 0;
+  }
   WgradParams& p = l->p;
   memset(&p, 0, sizeof(p));
   REFID_REQUIRE(d.nsrc == 1 || (d.nsrc == 2 && !tt.parity_mode), "build_wgrad: dual source not allowed with parity views");

@@ -1,6 +1,7 @@
 // Host-side description of one convolution-shaped op and its lowering onto the tap-GEMM / wgrad kernels.
 #pragma once
 #include "haloconv.cuh"
+#include "halowgrad.cuh"
 #include "tapgemm.cuh"
 #include "wgrad.cuh"
 
@@ -58,10 +59,14 @@ inline int run_conv(TapGemmLaunch& l, cudaStream_t s) {
 struct WgradLaunch {
   WgradParams p;
   int pixel_chunks;
+  int use_halo;  // stride-1 3x3 with 64-channel-multiple operands runs on the halo-wgrad kernel
+  HaloWgradParams hp;
 };
 // d describes the tapped operand P (kind, sources, taps); q is the un-shifted operand on the op's output grid.
 // out: fp32 [taps * sum(src C)][q.C], accumulated atomically.
 int build_wgrad(const ConvDesc& d, ActSrc q, float* out, WgradLaunch* l);
-inline int run_wgrad(WgradLaunch& l, cudaStream_t s) { return launch_wgrad(l.p, l.pixel_chunks, s); }
+inline int run_wgrad(WgradLaunch& l, cudaStream_t s) {
+  return l.use_halo ? launch_halowgrad(l.hp, s) : launch_wgrad(l.p, l.pixel_chunks, s);
+}
 
 }  // namespace refid

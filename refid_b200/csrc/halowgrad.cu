@@ -1,0 +1,240 @@
+// Halo-wgrad: weight gradient of the stride-1 3x3 convolutions with ONE activation-patch load per pixel tile.
+//
+//   D[(tap, ci)][co] += sum_pixels X[p + tap][ci] * G[p][co]
+//
+// The generic wgrad kernel (wgrad.cu) fetches a separate 128-pixel box of X per tap (9x the input from L2) and re-reads G
+// for every M tile.  Here a CTA owns a JOB -- a fixed set of accumulator tiles that fills TMEM -- and streams pixel
+// tiles (8 wide x 16 tall) through it: per tile one TMA box with the halo patch of X and one with G; every tap is a
+// shifted UMMA descriptor into the patch (both operands MN-major, K = pixels, two 8-pixel rows per K=16 step).
+//
+//   MODE 64  (Cout = 64):   job = one 64-channel slab of X, all 9 taps.  An MMA has M = 128 = TWO TAPS: the descriptor's
+//            leading-dimension byte offset (the stride between the two 64-row halves of A) is simply the address
+//            difference of the two taps inside the patch.  5 MMA groups (4 pairs + the last tap), N = 64, 320 TMEM columns.
+//   MODE 128 (Cout % 128 == 0): job = (pair of X slabs, one kernel row dy, 128-channel block of Cout).  M = 128 = the two
+//            slabs (LBO = slab stride in shared memory), one MMA group per dx, N = 128, 384 TMEM columns.
+//
+// Accumulation stays in TMEM over the CTA's whole pixel range (all T*B images of the batched launch); the fp32 result is
+// added to global memory once per CTA with vectorised reductions.
+#include "halowgrad.cuh"
+
+namespace refid {
+
+namespace {
+
+constexpr int kHWThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
+constexpr int kHWMaxStages = 6;
+constexpr uint32_t PITCH = 10;   // patch pixels per row (8 + 2 halo columns)
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int MODE>
+struct HWCfg;
+template <>
+struct HWCfg<64> {
+  static constexpr int ROWS = 18;                           // patch rows (16 + 2 halo rows)
+  static constexpr uint32_t P_BYTES = 18 * PITCH * 128;     // one slab patch (23040 B)
+  static constexpr uint32_t P_ALLOC = 23552;                // 1024-aligned
+  static constexpr uint32_t Q_BYTES = 128 * 64 * 2;         // 16 KB
+  static constexpr uint32_t STAGE = P_ALLOC + Q_BYTES;      // 39936
+  static constexpr uint32_t TX = P_BYTES + Q_BYTES;
+  static constexpr int GROUPS = 5, N = 64, COLS = 512;      // 320 used
+};
+template <>
+struct HWCfg<128> {
+  static constexpr int ROWS = 16;
+  static constexpr uint32_t P_BYTES = 16 * PITCH * 128;     // 20480 B per slab (1024-aligned)
+  static constexpr uint32_t P_ALLOC = 2 * P_BYTES;          // slab pair
+  static constexpr uint32_t Q_BYTES = 2 * 128 * 64 * 2;     // two 64-channel halves of the 128-channel block
+  static constexpr uint32_t STAGE = P_ALLOC + Q_BYTES;      // 73728
+  static constexpr uint32_t TX = P_ALLOC + Q_BYTES;
+  static constexpr int GROUPS = 3, N = 128, COLS = 512;     // 384 used
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_constant__ HaloWgradParams p) {
+  using Cfg = HWCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.num_stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)S * Cfg::STAGE);
+  uint64_t* empty_bar = full_bar + kHWMaxStages;
+  uint64_t* acc_bar = empty_bar + kHWMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  // job / pixel-range decode (consecutive CTAs = same pixel range, different jobs: they share the tile loads in L2)
+  const int job = blockIdx.x % p.jobs;
+  const int chunk = blockIdx.x / p.jobs;
+  const int t_begin = (int)(((long)p.num_tiles * chunk) / p.chunks);
+  const int t_end = (int)(((long)p.num_tiles * (chunk + 1)) / p.chunks);
+  int slab, dy = 0, coblk = 0;  // slab: global 64-channel slab index (MODE 64) or first slab of the pair (MODE 128)
+  if (MODE == 64) {
+    slab = job;
+  } else {
+    const int pairs = p.total_slabs / 2;
+    slab = (job % pairs) * 2;
+    dy = (job / pairs) % 3 - 1;
+    coblk = job / (pairs * 3);
+  }
+  const int src = slab >= p.src_slabs[0] ? 1 : 0;
+  const int slab_in_src = slab - (src ? p.src_slabs[0] : 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHWMaxStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (t_end > t_begin) {
+    if (warp == 0) {
+      // ---------------- TMA producer ----------------
+      if (elect_one()) {
+        tma_prefetch_desc(&p.tmP[src]);
+        tma_prefetch_desc(&p.tmQ);
+      }
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int x0 = (t % p.tiles_x) * 8;
+        const int y0 = ((t / p.tiles_x) % p.tiles_y) * 16;
+        const int n = t / tiles_per_img;
+        const int s = it % S;
+        mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1, 0x800 + s);
+        if (elect_one()) {
+          uint8_t* st = smem + (size_t)s * Cfg::STAGE;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::TX);
+          if (MODE == 64) {
+            tma_load_4d(st, &p.tmP[src], &full_bar[s], slab_in_src * 64, x0 - 1, y0 - 1, n);
+            tma_load_4d(st + Cfg::P_ALLOC, &p.tmQ, &full_bar[s], 0, x0, y0, n);
+          } else {
+            tma_load_4d(st, &p.tmP[src], &full_bar[s], slab_in_src * 64, x0 - 1, y0 + dy, n);
+            tma_load_4d(st + Cfg::P_BYTES, &p.tmP[src], &full_bar[s], slab_in_src * 64 + 64, x0 - 1, y0 + dy, n);
+            tma_load_4d(st + Cfg::P_ALLOC, &p.tmQ, &full_bar[s], coblk * 128, x0, y0, n);
+            tma_load_4d(st + Cfg::P_ALLOC + 16384, &p.tmQ, &full_bar[s], coblk * 128 + 64, x0, y0, n);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = smem_u32(smem);
+      constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::N, 1, 1);
+      constexpr uint32_t SBO_A = PITCH * 128;  // next 8-pixel K group = next tile row of the patch
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int s = it % S;
+        mbar_wait(&full_bar[s], (it / S) & 1, 0x810 + s);
+        tc_fence_after();
+        const uint32_t st = smem_u + (uint32_t)s * Cfg::STAGE;
+        // B: G tile [128 px][64 co] per half; K step = 16 pixel rows of 128 B = 2048 B; halves 16 KB apart
+        const uint64_t bd0 = make_smem_desc(st + Cfg::P_ALLOC, 16384, 1024, 2u);
+        if (elect_one()) {
+          if (MODE == 64) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+              for (int g = 0; g < 5; ++g) {
+                const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
+                const uint32_t offa = (uint32_t)((2 * ks + ta / 3) * (int)PITCH + ta % 3) * 128u;
+                const uint32_t offb = (uint32_t)((2 * ks + tb / 3) * (int)PITCH + tb % 3) * 128u;
+                const uint32_t lbo = g < 4 ? offb - offa : 128u;  // group 4: second half is a don't-care copy
+                const uint64_t ad = make_smem_desc(st + offa, lbo, SBO_A, 2u);
+                umma_bf16(tm + (uint32_t)(g * 64), ad, bd0 + (uint64_t)(ks * 128), IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g) {
+                const uint32_t offa = (uint32_t)((2 * ks) * (int)PITCH + g) * 128u;
+                const uint64_t ad = make_smem_desc(st + offa, Cfg::P_BYTES, SBO_A, 2u);
+                umma_bf16(tm + (uint32_t)(g * 128), ad, bd0 + (uint64_t)(ks * 128), IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (t == t_end - 1) umma_commit(acc_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ---------------- epilogue: TMEM -> fp32 global reductions, once per CTA ----------------
+      const int q = warp & 3;
+      const int m = q * 32 + lane;  // accumulator row
+      mbar_wait(acc_bar, 0, 0x820);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < Cfg::GROUPS; ++g) {
+        long row;
+        bool valid = true;
+        if (MODE == 64) {
+          const int tap = m < 64 ? 2 * g : 2 * g + 1;
+          valid = tap < 9;
+          row = (long)tap * p.cp_total + slab * 64 + (m & 63);
+        } else {
+          const int tap = (dy + 1) * 3 + g;
+          row = (long)tap * p.cp_total + slab * 64 + m;
+        }
+        float* orow = p.out + row * p.CQ + coblk * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < Cfg::N; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * Cfg::N + c0), v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) red_add_v4(orow + c0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::COLS);
+  }
+}
+
+template <int MODE>
+int launch_hw_inst(HaloWgradParams& p, cudaStream_t stream) {
+  using Cfg = HWCfg<MODE>;
+  static bool configured = false;
+  if (!configured) {
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(halowgrad_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  int stages = (int)((220 * 1024) / Cfg::STAGE);
+  if (stages > kHWMaxStages) stages = kHWMaxStages;
+  p.num_stages = stages;
+  const size_t smem = (size_t)stages * Cfg::STAGE + (2 * kHWMaxStages + 1) * sizeof(uint64_t) + 16 + 1024;
+  halowgrad_kernel<MODE><<<p.jobs * p.chunks, kHWThreads, smem, stream>>>(p);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int launch_halowgrad(HaloWgradParams& p, cudaStream_t stream) {
+  return p.mode == 64 ? launch_hw_inst<64>(p, stream) : launch_hw_inst<128>(p, stream);
+}
+
+}  // namespace refid

@@ -4,6 +4,7 @@
 #include "tapgemm.cu"
 #include "haloconv.cu"
 #include "wgrad.cu"
+#include "halowgrad.cu"
 #include "convop.cu"
 #include "elementwise.cu"
 #include "engine.cu"

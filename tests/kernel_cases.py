@@ -213,6 +213,9 @@ CASES = {
     "wgrad3x3_128_128": lambda: case_wgrad3x3(cin=128, cout=128, H=8, W=8),
     "wgrad3x3_256_256": lambda: case_wgrad3x3(cin=256, cout=256, H=8, W=8),
     "wgrad3x3_ragged": lambda: case_wgrad3x3(H=24, W=20, N=3),
+    "wgrad3x3_dual_128+128_128_ragged": lambda: case_wgrad3x3(cin=128, cout=128, cin2=128, H=24, W=12, N=3),
+    "wgrad3x3_128_256": lambda: case_wgrad3x3(cin=128, cout=256, H=16, W=24, N=2),
+    "wgrad3x3_64_64_many_tiles": lambda: case_wgrad3x3(H=64, W=64, N=5),
     "wgrad1x1_128_64": lambda: case_wgrad1x1(),
     "wgrad_down4_64": lambda: case_wgrad_down4(),
     "wgrad_up2_128_64": lambda: case_wgrad_up2(),
