@@ -76,8 +76,8 @@ int fill_taps(int kind, int parity, TapTable* t) {
 }  // namespace
 
 // 4-D NHWC map whose box is the halo patch of one 8 x (16*NM) pixel tile: (64 channels, pitch_px, patch_rows, 1 image).
-static int make_patch_map(CUtensorMap* m, const ActSrc& s, int N, int H, int W, int pitch_px, int patch_rows) {
-  return make_act_map(m, s.ptr, N, H, W, s.pitch, s.C, 0, 0, 1, 64, pitch_px, patch_rows, 1);
+static int make_patch_map(CUtensorMap* m, const ActSrc& s, int N, int H, int W, int pitch_px, int patch_rows, int kc) {
+  return make_act_map(m, s.ptr, N, H, W, s.pitch, s.C, 0, 0, 1, kc, pitch_px, patch_rows, 1);
 }
 
 // Returns 1 when the op was lowered onto the halo-conv engine, 0 when it does not qualify, -1 on error.
@@ -85,9 +85,10 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   if (d.kind != CK_3X3 && d.kind != CK_1X1) return 0;
   static const int disabled = getenv("REFID_NO_HALO") ? 1 : 0;
   if (disabled) return 0;
-  int ktot = 0;
+  int ktot = 0, kc = 64;
   for (int s = 0; s < d.nsrc; ++s) {
-    if (d.src[s].C % 64) return 0;
+    if (d.src[s].C % 32) return 0;
+    if (d.src[s].C % 64) kc = 32;  // 32-channel slabs: 64-byte pixel rows, 64B swizzle
     ktot += d.src[s].C;
   }
   if (ktot != d.w_cols) return 0;
@@ -98,7 +99,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     int c = groups[g].channels & -groups[g].channels;  // largest power of two dividing the group
     if (c < seg) seg = c;
   }
-  int BN = 256;
+  int BN = kc == 64 ? 256 : 128;
   while (BN > 32 && total % BN) BN >>= 1;
   if (total % BN) return 0;
   if (seg > BN) seg = BN;
@@ -111,7 +112,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.wrows_per_tap = d.wrows_per_tap;
   h.w_row0 = d.w_row0;
   h.nsrc = d.nsrc;
-  for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / 64;
+  h.kc = kc;
+  for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / kc;
   h.n_blocks = total / BN;
   h.epi_seg = seg;
   h.epi_shift = 0;
@@ -128,8 +130,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.tiles_y = (d.H + 16 * NM - 1) / (16 * NM);
   h.num_items = h.tiles_x * h.tiles_y * d.N * h.n_blocks;
   for (int s = 0; s < d.nsrc; ++s)
-    if (make_patch_map(&h.tmA[s], d.src[s], d.N, d.H, d.W, h.pitch_px, h.patch_rows)) return -1;
-  if (make_mat_map(&h.tmB, d.w, d.w_rows, d.w_cols, 64, BN)) return -1;
+    if (make_patch_map(&h.tmA[s], d.src[s], d.N, d.H, d.W, h.pitch_px, h.patch_rows, kc)) return -1;
+  if (make_mat_map(&h.tmB, d.w, d.w_rows, d.w_cols, kc, BN)) return -1;
   int nd = 0;
   for (int g = 0; g < ngroups; ++g)
     for (int c = 0; c < groups[g].channels; c += seg) {

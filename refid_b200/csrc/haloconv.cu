@@ -153,19 +153,23 @@ __device__ __forceinline__ void epi_apply32_pf(const EpiDesc& e, float* v, size_
 // so the single issuing thread has <= 62 cycles per MMA at N <= 128.  The producer and MMA warps therefore run their
 // loops warp-uniformly (warp index via shuffle, elect.sync only around the issue) so that descriptors live in uniform
 // registers, and every per-MMA descriptor is `base + compile-time constant` (TAPS / pitch / NM are template parameters).
-template <int BN, int NM, int TAPS>
+template <int BN, int NM, int TAPS, int KC>
 __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PITCH = TAPS == 9 ? 10 : 8;       // pixels per patch row in shared memory
   constexpr int PATCH_ROWS = 16 * NM + 2 * HALO;
   constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
-  constexpr uint32_t B_TILE = BN * 128;        // bytes of one (tap, 64-channel slab) weight tile
+  constexpr uint32_t PXB = KC * 2;             // bytes of one pixel row of a K slab (KC = 64 or 32 channels)
+  constexpr uint32_t SWZ = KC == 64 ? 2u : 4u;  // UMMA layout type: 128B / 64B swizzle
+  constexpr int KSTEPS = KC / 16;
+  constexpr uint32_t B_TILE = BN * PXB;        // bytes of one (tap, slab) weight tile
+  constexpr uint32_t SBO_B = 8u * PXB;
   constexpr uint32_t ACC_COLS = NM * BN;       // TMEM columns of one accumulator buffer
   constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) <= 32 ? 32 : ((2 * ACC_COLS) <= 64 ? 64 : ((2 * ACC_COLS) <= 128 ? 128 : ((2 * ACC_COLS) <= 256 ? 256 : 512)));
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
-  constexpr uint32_t A_TX = (uint32_t)PATCH_ROWS * PITCH * 128u;
+  constexpr uint32_t A_TX = (uint32_t)PATCH_ROWS * PITCH * PXB;
   constexpr uint32_t A_BYTES = (A_TX + 1023u) & ~1023u;
-  constexpr uint32_t SBO = (uint32_t)PITCH * 128u;  // 8-pixel group (one tile row) to the next tile row
+  constexpr uint32_t SBO = (uint32_t)PITCH * PXB;  // 8-pixel group (one tile row) to the next tile row
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         mbar_arrive_expect_tx(wres_bar, (uint32_t)b_total);
         for (int ks = 0; ks < total_slabs; ++ks)
           for (int tap = 0; tap < TAPS; ++tap)
-            tma_load_2d(b_base + (size_t)(ks * TAPS + tap) * B_TILE, &p.tmB, wres_bar, ks * 64, p.w_row0 + tap * p.wrows_per_tap);
+            tma_load_2d(b_base + (size_t)(ks * TAPS + tap) * B_TILE, &p.tmB, wres_bar, ks * KC, p.w_row0 + tap * p.wrows_per_tap);
       }
     }
     uint32_t ia = 0, ib = 0;
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           mbar_wait(&a_empty[sa], ((ia / SA) & 1) ^ 1, 0x700 + sa);
           if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[sa], A_TX);
-            tma_load_4d(a_base + (size_t)sa * A_BYTES, &p.tmA[src], &a_full[sa], slab * 64, x0 - HALO, y0 - HALO, n);
+            tma_load_4d(a_base + (size_t)sa * A_BYTES, &p.tmA[src], &a_full[sa], slab * KC, x0 - HALO, y0 - HALO, n);
           }
           ++ia;
           if (!p.resident_b) {
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
               mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1, 0x710 + sb);
               if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[sb], B_TILE);
-                tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * 64, p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
+                tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * KC, p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
               }
               ++ib;
             }
@@ -271,19 +275,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         const int sa = ia % SA;
         mbar_wait(&a_full[sa], (ia / SA) & 1, 0x740 + sa);
         tc_fence_after();
-        const uint64_t a_desc0 = make_smem_desc(a_base_u + (uint32_t)sa * A_BYTES, 16, SBO, 2u);
+        const uint64_t a_desc0 = make_smem_desc(a_base_u + (uint32_t)sa * A_BYTES, 16, SBO, SWZ);
         if (p.resident_b) {
-          const uint64_t b_desc0 = make_smem_desc(b_base_u + (uint32_t)(ks * TAPS) * B_TILE, 16, 1024, 2u);
+          const uint64_t b_desc0 = make_smem_desc(b_base_u + (uint32_t)(ks * TAPS) * B_TILE, 16, SBO_B, SWZ);
           if (elect_one()) {
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) {
               constexpr int dummy = 0;
               (void)dummy;
-              const uint32_t tap_off = (uint32_t)(((TAPS == 9 ? tap / 3 : 0)) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * 128u;
+              const uint32_t tap_off = (uint32_t)(((TAPS == 9 ? tap / 3 : 0)) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * PXB;
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < KSTEPS; ++k) {
                   const uint64_t ad = a_desc0 + (uint64_t)((tap_off + (uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
                   const uint64_t bd = b_desc0 + (uint64_t)(((uint32_t)tap * B_TILE + (uint32_t)k * 32u) >> 4);
                   umma_bf16(acc + j * BN, ad, bd, IDESC, (ks > 0 || tap > 0 || k > 0) ? 1u : 0u);
@@ -299,14 +303,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
             const int sb = ib % SB;
             mbar_wait(&b_full[sb], (ib / SB) & 1, 0x750 + sb);
             tc_fence_after();
-            const uint32_t tap_off = (uint32_t)((TAPS == 9 ? tap / 3 : 0) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * 128u;
+            const uint32_t tap_off = (uint32_t)((TAPS == 9 ? tap / 3 : 0) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * PXB;
             const uint64_t a_desc = a_desc0 + (uint64_t)(tap_off >> 4);
-            const uint64_t b_desc = make_smem_desc(b_base_u + (uint32_t)sb * B_TILE, 16, 1024, 2u);
+            const uint64_t b_desc = make_smem_desc(b_base_u + (uint32_t)sb * B_TILE, 16, SBO_B, SWZ);
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < KSTEPS; ++k) {
                   const uint64_t ad = a_desc + (uint64_t)(((uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
                   const uint64_t bd = b_desc + (uint64_t)(((uint32_t)k * 32u) >> 4);
                   umma_bf16(acc + j * BN, ad, bd, IDESC, (ks > 0 || tap > 0 || k > 0) ? 1u : 0u);
@@ -401,17 +405,17 @@ constexpr size_t kHaloSmemMax = 227 * 1024;
 constexpr size_t kHaloBarBytes = (4 * kHaloMaxStages + 5) * sizeof(uint64_t) + 16;
 
 size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
-  const size_t a_bytes = ((size_t)p.patch_rows * p.pitch_px * 128 + 1023) & ~(size_t)1023;
+  const size_t a_bytes = ((size_t)p.patch_rows * p.pitch_px * p.kc * 2 + 1023) & ~(size_t)1023;
   const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
-  const size_t b_total = p.resident_b ? (size_t)total_slabs * p.num_taps * BN * 128 : (size_t)p.stages_b * BN * 128;
+  const size_t b_total = p.resident_b ? (size_t)total_slabs * p.num_taps * BN * p.kc * 2 : (size_t)p.stages_b * BN * p.kc * 2;
   return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + 1024;
 }
 
-template <int BN, int NM, int TAPS>
+template <int BN, int NM, int TAPS, int KC>
 int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
     configured = true;
   }
   static int num_sms = 0;
@@ -421,7 +425,7 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
     REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  haloconv_kernel<BN, NM, TAPS><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
+  haloconv_kernel<BN, NM, TAPS, KC><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -457,11 +461,17 @@ int haloconv_plan(HaloConvParams* p, int BN, int NM) {
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream) {
   REFID_REQUIRE((p.num_taps == 9 && p.halo == 1 && p.pitch_px == 10) || (p.num_taps == 1 && p.halo == 0 && p.pitch_px == 8),
                 "haloconv: taps/halo/pitch %d/%d/%d unsupported", p.num_taps, p.halo, p.pitch_px);
-#define HINST(bn, nm)                                                             \
-  if (BN == bn && NM == nm)                                                       \
-    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9>(p, stream) : launch_halo_inst<bn, nm, 1>(p, stream);
+#define HINST(bn, nm)                                                                                        \
+  if (BN == bn && NM == nm && p.kc == 64)                                                                   \
+    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9, 64>(p, stream) : launch_halo_inst<bn, nm, 1, 64>(p, stream);
+#define HINST32(bn, nm)                                                                                      \
+  if (BN == bn && NM == nm && p.kc == 32)                                                                   \
+    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9, 32>(p, stream) : launch_halo_inst<bn, nm, 1, 32>(p, stream);
   HINST(32, 1) HINST(64, 1) HINST(128, 1) HINST(256, 1)
   HINST(32, 2) HINST(64, 2) HINST(128, 2)
+  HINST32(32, 1) HINST32(64, 1) HINST32(128, 1)
+  HINST32(32, 2) HINST32(64, 2) HINST32(128, 2)
+#undef HINST32
 #undef HINST
   set_error("haloconv: unsupported BN=%d NM=%d", BN, NM);
   return 1;

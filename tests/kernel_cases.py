@@ -195,6 +195,10 @@ CASES = {
     "conv3x3_dual_64+64_64": lambda: case_conv3x3(cin2=64, pre=True),
     "conv3x3_32_64_bk32": lambda: case_conv3x3(cin=32),
     "conv3x3_dual_32+32_32": lambda: case_conv3x3(cin=32, cin2=32, cout=32),
+    "conv3x3_32_32_ragged_pre": lambda: case_conv3x3(cin=32, cout=32, H=40, W=28, N=3, pre=True),
+    "conv3x3_32_128_big": lambda: case_conv3x3(cin=32, cout=128, H=64, W=48, N=2),
+    "conv3x3_96_64": lambda: case_conv3x3(cin=96, cout=64, H=24, W=24),
+    "dgrad3x3_split_32": lambda: case_dgrad3x3_split(c=32),
     "conv3x3_128_128": lambda: case_conv3x3(cin=128, cout=128, H=8, W=8),
     "conv3x3_256_256_h4": lambda: case_conv3x3(cin=256, cout=256, H=4, W=4, N=3),
     "conv3x3_ragged_24x20": lambda: case_conv3x3(H=24, W=20, N=1),
