@@ -250,6 +250,8 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
 // Returns 1 when lowered onto the halo-wgrad kernel, 0 when the op does not qualify, -1 on error.
 static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
   if (d.kind != CK_3X3) return 0;
+  for (int s = 0; s < d.nsrc; ++s)
+    if (d.src[s].nmod) return 0;
   static const int disabled = getenv("REFID_NO_HALO_WGRAD") ? 1 : 0;
   if (disabled) return 0;
   int mode = 0;
@@ -331,7 +333,12 @@ int build_wgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
     p.tap_map[i] = (signed char)tt.map[i];
   }
   p.nsrc = d.nsrc;
-  for (int s = 0; s < d.nsrc; ++s) p.src_blocks[s] = d.src[s].C / CB;
+  for (int s = 0; s < d.nsrc; ++s) {
+    p.src_blocks[s] = d.src[s].C / CB;
+    p.src_nmod[s] = d.src[s].nmod;
+    REFID_REQUIRE(!d.src[s].nmod || (!tt.parity_mode && d.src[s].nmod % p.TN == 0),
+                  "build_wgrad: repeated source needs image-aligned tiles (nmod %d, TN %d)", d.src[s].nmod, p.TN);
+  }
   p.CB = CB;
   p.CBq = CBq;
   p.CQ = q.C;
@@ -351,7 +358,8 @@ int build_wgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
         return 1;
   } else {
     for (int s = 0; s < d.nsrc; ++s)
-      if (make_act_map(&p.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, CB, p.TW, p.TH, p.TN))
+      if (make_act_map(&p.tmP[s], d.src[s].ptr, d.src[s].nmod ? d.src[s].nmod : d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0,
+                       0, 1, CB, p.TW, p.TH, p.TN))
         return 1;
   }
   if (make_act_map(&p.tmQ, q.ptr, d.N, gh, gw, q.pitch, q.C, 0, 0, 1, CBq, p.TW, p.TH, p.TN)) return 1;

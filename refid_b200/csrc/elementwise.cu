@@ -581,6 +581,31 @@ int launch_colsum(const __nv_bfloat16* in, long rows, int C, float* out, cudaStr
   return 0;
 }
 
+__global__ void __launch_bounds__(kEwThreads) k_sum_series(const __nv_bfloat16* __restrict__ base, long slot_elems, int T,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const long n8 = slot_elems / 8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+      float u[8];
+      load8(base + (size_t)t * slot_elems + i * 8, u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += u[k];
+    }
+    store8(out + i * 8, v);
+  }
+}
+
+int launch_sum_series(const __nv_bfloat16* base, long slot_elems, int T, __nv_bfloat16* out, cudaStream_t s) {
+  REFID_REQUIRE(slot_elems % 8 == 0, "sum_series: slot_elems=%ld not a multiple of 8", slot_elems);
+  unsigned blocks = blocks_for(slot_elems / 8, kEwThreads);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  k_sum_series<<<blocks, kEwThreads, 0, s>>>(base, slot_elems, T, out);
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int launch_addmask(const AddMaskArgs& a, cudaStream_t s) {
   REFID_REQUIRE(a.n % 8 == 0, "addmask: n=%ld not a multiple of 8", a.n);
   unsigned blocks = blocks_for(a.n / 8, kEwThreads);

@@ -67,6 +67,7 @@ struct Series {
   long base = -1;       // byte offset of slot 0 in the workspace
   size_t slot_bytes = 0;
   long gbase = -1;      // persistent gradient (dL/dZ) array, allocated when the producing site's wgrad is batched
+  bool need_g = false;  // ... or when a deferred gradient needs all T output gradients at once
 };
 
 struct GBuf {
@@ -87,6 +88,7 @@ struct ConvOp {
   bool nchw_out = false;       // pred: fp32 NCHW store into the caller's output tensor
   long nchw_toff = 0, nchw_nstride = 0;
   bool no_tape = false;
+  bool defer_in1 = false;  // in[1] is the same tensor at every step: its gradient is computed once from the summed dL/dZ
 };
 
 typedef std::function<int(cudaStream_t)> Launch;
@@ -137,6 +139,7 @@ struct Engine {
   std::string cur_sdir;    // "b" / "f": sweep the current step belongs to
   std::vector<std::vector<ConvOp>> site_calls;  // forward conv calls per site (plan time)
   std::vector<char> site_batched;               // weight/bias gradient of this site is one batched launch
+  std::vector<int> site_rep;                    // bit k: input k of the batched site is ONE tensor repeated every step
 
   // per-call io
   const float* io_x = nullptr;
@@ -658,6 +661,7 @@ struct Engine {
       tape.push_back([self, op]() { return self->conv_bwd(op); });
       if (site_calls.size() < sites.size()) site_calls.resize(sites.size());
       site_calls[op.site].push_back(op);
+      if (op.defer_in1 && op.out >= 0 && tens[op.out].series >= 0) series[tens[op.out].series].need_g = true;
     }
     return op.out2 >= 0 && op.out < 0 ? op.out2 : op.out;
   }
@@ -733,7 +737,7 @@ struct Engine {
     if (s.dgrad_off >= 0) {
       int k = 0, chan0 = 0;
       while (k < op.nin) {
-        if (!tens[op.in[k]].need_grad) {
+        if (!tens[op.in[k]].need_grad || (k == 1 && op.defer_in1)) {
           chan0 += tens[op.in[k]].C;
           ++k;
           continue;
@@ -742,7 +746,7 @@ struct Engine {
         OutGroup groups[2];
         memset(groups, 0, sizeof(groups));
         int ng = 0, w_row0 = chan0, grad_ch = 0;
-        while (k < op.nin && tens[op.in[k]].need_grad) {
+        while (k < op.nin && tens[op.in[k]].need_grad && !(k == 1 && op.defer_in1)) {
           Target t;
           if (target(op.in[k], &t)) return 1;
           OutGroup& g = groups[ng++];
@@ -1162,8 +1166,19 @@ struct Engine {
       }
     }
     cur_slot = -1;
-    // Only the FINAL backward state reaches the forward sweep (list aliasing at :181).
-    for (int l = 0; l < 3; ++l) mark_f32acc(hb[l]);
+    // Only the FINAL backward state reaches the forward sweep (list aliasing at :181): W_h . h_b is
+    // linear in a tensor that is the same at all T steps, so its gradient is W_h^T . (sum_t dL/dZ_t) -- ONE 1x1
+    // data-gradient GEMM per level on the summed output gradients of fuse_two_dir, placed on the tape between the two
+    // sweeps (i.e. after the whole forward sweep has been back-propagated, before the backward sweep's BPTT starts).
+    if (train) {
+      const int hb0 = hb[0], hb1 = hb[1], hb2 = hb[2];
+      tape.push_back([self, hb0, hb1, hb2]() {
+        const int hbs[3] = {hb0, hb1, hb2};
+        for (int l = 0; l < 3; ++l)
+          if (self->deferred_state_grad(l, hbs[l])) return 1;
+        return 0;
+      });
+    }
     // ---- forward sweep t = 0 .. T-1 (:185-216)
     int hf[3], sd[3], hf_series[3], sd_series[3];
     for (int l = 0; l < 3; ++l) hf_series[l] = state_series(H >> l, W >> l, (2 * b) << l, 0, &hf[l]);
@@ -1202,6 +1217,7 @@ struct Engine {
         cf.in[0] = h;
         cf.in[1] = hb[l];
         cf.nin = 2;
+        cf.defer_in1 = true;
         cf.act = ACT_LRELU;
         cf.slope = 0.2f;
         const int hfu = conv(cf);
@@ -1315,12 +1331,73 @@ struct Engine {
     return 0;
   }
 
+  int deferred_state_grad(int l, int hb_id) {
+    const int si = site("encoders_forward." + std::to_string(l) + ".fuse_two_dir");
+    if (si < 0) return 1;
+    const Site& s = sites[si];
+    const auto& calls = site_calls[si];
+    REFID_REQUIRE(!calls.empty(), "fuse_two_dir has no calls");
+    int lo = 1 << 30;
+    for (auto& c : calls) lo = tens[c.out].slot < lo ? tens[c.out].slot : lo;
+    const Ten o = tens[calls[0].out];
+    const Series& sr = series[o.series];
+    REFID_REQUIRE(sr.gbase >= 0 && (int)calls.size() == T, "fuse_two_dir gradients are not kept as a series");
+    cur_label = s.key;
+    const long slot_elems = (long)(sr.slot_bytes / 2);
+    const int tmp = galloc(sr.slot_bytes);
+    const __nv_bfloat16* gbase = P(sr.gbase + (long)lo * (long)sr.slot_bytes);
+    __nv_bfloat16* sum = P((long)gbufs[tmp].off);
+    const int steps = T;
+    emit([gbase, slot_elems, steps, sum](cudaStream_t st) { return launch_sum_series(gbase, slot_elems, steps, sum, st); },
+         LC_OTHER, 0.0, ":sum_gz");
+    Target t;
+    if (target(hb_id, &t)) return 1;
+    if (!dry) {
+      const int c = o.C;  // fuse: (h | h_b) 2c -> c; the data-gradient pack is [2c rows][c cols], h_b rows start at c
+      OutGroup g;
+      memset(&g, 0, sizeof(g));
+      g.channels = tens[hb_id].C;
+      g.epi.out = t.dst;
+      g.epi.pre = t.pre;
+      g.epi.pre2 = t.pre2;
+      g.epi.sv = t.sv;
+      g.epi.act = t.act;
+      g.epi.slope = t.slope;
+      g.epi.out_f32 = t.dstf;
+      g.epi.C = t.pitch;
+      ConvDesc d;
+      memset(&d, 0, sizeof(d));
+      d.kind = CK_1X1;
+      d.src[0] = {sum, c, c, 0};
+      d.nsrc = 1;
+      d.N = o.N;
+      d.H = o.H;
+      d.W = o.W;
+      d.w = wpackb + s.dgrad_off;
+      d.w_cols = c;
+      d.w_rows = 2L * c;
+      d.wrows_per_tap = 2 * c;
+      d.w_row0 = c;
+      TapGemmLaunch lch;
+      if (build_conv(d, &g, 1, &lch)) return 1;
+      emit([lch](cudaStream_t st) mutable { return run_conv(lch, st); }, LC_CONV_DGRAD,
+           2.0 * (double)o.N * o.H * o.W * c * c * T, ":dgrad_hb");
+    }
+    release_consumed();
+    gunref(tmp);
+    cur_label = "";
+    return 0;
+  }
+
   // A site called once per time step with contiguous per-step operands gets ONE weight/bias-gradient launch over all
   // T*B images; its per-step output gradients are then kept in a persistent series array instead of the pool.
   void decide_batching() {
     site_batched.assign(sites.size(), 0);
+    site_rep.assign(sites.size(), 0);
     site_calls.resize(sites.size());
     if (!train) return;
+    for (auto& sr : series)
+      if (sr.need_g && sr.gbase < 0) sr.gbase = act_alloc(sr.slot_bytes * (size_t)(T + 1));
     static const bool disabled = getenv("REFID_NO_BATCHED_WGRAD") != nullptr;
     if (disabled) return;
     for (size_t si = 0; si < sites.size(); ++si) {
@@ -1332,6 +1409,15 @@ struct Engine {
       if (!ok) continue;
       std::sort(calls.begin(), calls.end(), [&](const ConvOp& a, const ConvOp& b2) { return tens[a.out].slot < tens[b2.out].slot; });
       const Ten o0 = tens[calls[0].out];
+      int rep = 0;
+      for (int k = 0; k < calls[0].nin; ++k)
+        if (calls.size() > 1 && tens[calls[1].in[k]].off == tens[calls[0].in[k]].off) {
+          // the same tensor at every step (the final backward state in fuse_two_dir): repeat it along the image axis
+          const Ten& a0 = tens[calls[0].in[k]];
+          int tw, th, tn;
+          pick_tile(a0.N, a0.H, a0.W, &tw, &th, &tn);
+          if (calls[0].kind == CK_1X1 && a0.N % tn == 0) rep |= 1 << k;
+        }
       for (size_t i = 0; i < calls.size() && ok; ++i) {
         const Ten& o = tens[calls[i].out];
         if (o.series != o0.series || o.slot != o0.slot + (int)i || calls[i].nin != calls[0].nin ||
@@ -1342,12 +1428,13 @@ struct Engine {
           const Ten& a = tens[calls[i].in[k]];
           const long stride = (long)a0.N * a0.H * a0.W * a0.pitch * 2;
           if (a.C != a0.C || a.pitch != a0.pitch || a.N != a0.N || a.H != a0.H || a.W != a0.W ||
-              a.off != a0.off + (long)i * stride)
+              a.off != a0.off + ((rep >> k) & 1 ? 0 : (long)i * stride))
             ok = false;
         }
       }
       if (!ok) continue;
       site_batched[si] = 1;
+      site_rep[si] = rep;
       Series& sr = series[o0.series];
       if (sr.gbase < 0) sr.gbase = act_alloc(sr.slot_bytes * (size_t)(T + 1));
     }
@@ -1384,7 +1471,7 @@ struct Engine {
         d.nsrc = op.nin;
         for (int k = 0; k < op.nin; ++k) {
           const Ten& t = tens[op.in[k]];
-          d.src[k] = {P(t.off), t.C, t.pitch};
+          d.src[k] = {P(t.off), t.C, t.pitch, (site_rep[si] >> k) & 1 ? t.N : 0};
         }
         d.N = n * in0.N;
         d.H = in0.H;

@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
                 cb -= p.src_blocks[0];
               }
               const CUtensorMap* pm = &p.tmP[p.parity_mode ? p.tap_map[tap] : src];
+              const int nmod = p.parity_mode ? 0 : p.src_nmod[src];
               tma_load_4d(p_dst + (size_t)j * 128 * p.CB * 2, pm, &full_bar[s], cb * p.CB, x0 + p.tap_dx[tap],
-                          y0 + p.tap_dy[tap], n0);
+                          y0 + p.tap_dy[tap], nmod ? n0 % nmod : n0);
             }
             const int nq = p.BNq / p.CBq;
             for (int j = 0; j < nq; ++j)

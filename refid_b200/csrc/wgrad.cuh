@@ -15,6 +15,7 @@ struct WgradParams {
   int num_taps;
   signed char tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_map[kMaxTaps];
   int nsrc, src_blocks[2];  // CB-channel blocks per P source
+  int src_nmod[2];          // P source s holds src_nmod[s] images that repeat along the launch's image axis (0: off)
   int parity_mode;
   int CB;           // channel block of P maps (64 or 32)
   int CBq;          // channel block of the Q map (64 or 32)
