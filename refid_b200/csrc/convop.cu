@@ -62,6 +62,9 @@ int fill_taps(int kind, int parity, TapTable* t) {
         }
       return 0;
     }
+    case CK_DOWN4_DGRAD_HALO:
+      set_error("CK_DOWN4_DGRAD_HALO needs 64-channel-multiple operands (halo-conv engine only)");
+      return 1;
     case CK_UP2_DGRAD:
       t->n = 4;
       t->parity_mode = 1;
@@ -82,7 +85,9 @@ static int make_patch_map(CUtensorMap* m, const ActSrc& s, int N, int H, int W, 
 
 // Returns 1 when the op was lowered onto the halo-conv engine, 0 when it does not qualify, -1 on error.
 static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out) {
-  if (d.kind != CK_3X3 && d.kind != CK_1X1) return 0;
+  const bool down_dgrad = d.kind == CK_DOWN4_DGRAD_HALO;
+  if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad) return 0;
+  if (down_dgrad && ngroups != 1) return 0;
   static const int disabled = getenv("REFID_NO_HALO") ? 1 : 0;
   if (disabled) return 0;
   int ktot = 0, kc = 64;
@@ -106,15 +111,30 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   if (BN % seg || (total / seg) > kMaxNBlocks) return 0;
   HaloConvParams& h = out->hp;
   memset(&h, 0, sizeof(h));
-  h.num_taps = d.kind == CK_3X3 ? 9 : 1;
-  h.halo = d.kind == CK_3X3 ? 1 : 0;
+  h.num_taps = d.kind == CK_1X1 ? 1 : 9;
+  h.halo = d.kind == CK_1X1 ? 0 : 1;
   h.pitch_px = h.halo ? 10 : 8;
   h.wrows_per_tap = d.wrows_per_tap;
   h.w_row0 = d.w_row0;
   h.nsrc = d.nsrc;
   h.kc = kc;
   for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / kc;
-  h.n_blocks = total / BN;
+  h.n_blocks = (down_dgrad ? 4 : 1) * (total / BN);
+  if (h.n_blocks > kMaxNBlocks || (down_dgrad && 4 * (total / seg) > kMaxNBlocks)) return 0;
+  if (down_dgrad) {
+    // N blocks enumerate (output parity q = qy*2+qx, channel block); parity q of dX[2i+qy][2j+qx] uses the taps (dy,dx) of
+    // the dY neighbourhood with ky = qy + 1 - 2*dy and kx = qx + 1 - 2*dx inside the 4x4 kernel
+    const int per_q = total / BN;
+    for (int nb = 0; nb < h.n_blocks; ++nb) {
+      const int qy = (nb / per_q) >> 1, qx = (nb / per_q) & 1;
+      unsigned m = 0;
+      for (int t9 = 0; t9 < 9; ++t9) {
+        const int ky = qy + 1 - 2 * (t9 / 3 - 1), kx = qx + 1 - 2 * (t9 % 3 - 1);
+        if (ky >= 0 && ky < 4 && kx >= 0 && kx < 4) m |= 1u << t9;
+      }
+      h.tap_mask[nb] = (unsigned short)m;
+    }
+  }
   h.epi_seg = seg;
   h.epi_shift = 0;
   while ((1 << h.epi_shift) < seg) ++h.epi_shift;
@@ -133,16 +153,18 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     if (make_patch_map(&h.tmA[s], d.src[s], d.N, d.H, d.W, h.pitch_px, h.patch_rows, kc)) return -1;
   if (make_mat_map(&h.tmB, d.w, d.w_rows, d.w_cols, kc, BN)) return -1;
   int nd = 0;
-  for (int g = 0; g < ngroups; ++g)
-    for (int c = 0; c < groups[g].channels; c += seg) {
-      EpiDesc e = groups[g].epi;
-      e.coff += c;
-      e.osy = e.osx = 1;
-      e.ooy = e.oox = 0;
-      e.OH = d.H;
-      e.OW = d.W;
-      h.epi[nd++] = e;
-    }
+  for (int q = 0; q < (down_dgrad ? 4 : 1); ++q)
+    for (int g = 0; g < ngroups; ++g)
+      for (int c = 0; c < groups[g].channels; c += seg) {
+        EpiDesc e = groups[g].epi;
+        e.coff += c;
+        e.osy = e.osx = down_dgrad ? 2 : 1;
+        e.ooy = down_dgrad ? (q >> 1) : 0;
+        e.oox = down_dgrad ? (q & 1) : 0;
+        e.OH = down_dgrad ? 2 * d.H : d.H;
+        e.OW = down_dgrad ? 2 * d.W : d.W;
+        h.epi[nd++] = e;
+      }
   out->use_halo = 1;
   out->BN = BN;
   out->BK = 64;
@@ -152,8 +174,6 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
 }
 
 int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out) {
-  TapTable tt;
-  if (fill_taps(d.kind, d.parity, &tt)) return 1;
   out->use_halo = 0;
   out->NM = 1;
   {
@@ -161,6 +181,8 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
     if (r < 0) return 1;
     if (r > 0) return 0;
   }
+  TapTable tt;
+  if (fill_taps(d.kind, d.parity, &tt)) return 1;
   TapGemmParams& p = out->p;
   memset(&p, 0, sizeof(p));
   REFID_REQUIRE(d.nsrc == 1 || (d.nsrc == 2 && !tt.parity_mode), "build_conv: dual source not allowed with parity views");

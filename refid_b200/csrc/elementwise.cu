@@ -535,6 +535,11 @@ __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ f
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int t = (int)(i / per_tap);
     const long r = i % per_tap;
+    const long dst = d.dst_off + (d.dst_tap_stride ? (long)t * d.dst_tap_stride + r : i);
+    if (d.tapmap[t] < 0) {
+      wpack[dst] = __float2bfloat16(0.f);
+      continue;
+    }
     long src;
     if (d.transpose) {  // dst [t][Cc][R]
       const int j = (int)(r / d.R), ii = (int)(r % d.R);
@@ -542,7 +547,7 @@ __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ f
     } else {
       src = (long)d.tapmap[t] * per_tap + r;
     }
-    wpack[d.dst_off + i] = __float2bfloat16(flat[d.src_off + src]);
+    wpack[dst] = __float2bfloat16(flat[d.src_off + src]);
   }
 }
 

@@ -170,6 +170,7 @@ struct Engine {
     const long n = (long)taps * R * Cc;
     auto add_pack = [&](int transpose, const int* tapmap) {
       PackDesc d;
+      memset(&d, 0, sizeof(d));
       d.src_off = s.w_off;
       d.dst_off = pack_elems;
       d.ntaps = taps;
@@ -202,7 +203,31 @@ struct Engine {
         break;
       case SK_DOWN4:
         if (fwd_pack) s.fwd_off = add_pack(1, ident);
-        if (dgrad_pack) s.dgrad_off = add_pack(0, down);
+        if (dgrad_pack) {
+          // data-gradient on the halo-conv engine: [tap9 of the dY neighbourhood][output parity q][Cin][Cout], zero blocks
+          // where the parity does not use the tap (ky = qy + 1 - 2*dy, kx = qx + 1 - 2*dx outside the 4x4 kernel)
+          s.dgrad_off = pack_elems;
+          for (int q = 0; q < 4; ++q) {
+            PackDesc d;
+            memset(&d, 0, sizeof(d));
+            d.src_off = s.w_off;
+            d.dst_off = pack_elems + (long)q * R * Cc;
+            d.ntaps = 9;
+            d.R = R;
+            d.Cc = Cc;
+            d.transpose = 0;
+            d.dst_tap_stride = 4L * R * Cc;
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const int ky = (q >> 1) + 1 - 2 * (t9 / 3 - 1), kx = (q & 1) + 1 - 2 * (t9 % 3 - 1);
+              d.tapmap[t9] = (signed char)((ky >= 0 && ky < 4 && kx >= 0 && kx < 4) ? ky * 4 + kx : -1);
+            }
+            packs.push_back(d);
+          }
+          const long n36 = 36L * R * Cc;
+          pack_elems = (pack_elems + n36 + 63) / 64 * 64;
+          if (9L * R * Cc > pack_max) pack_max = 9L * R * Cc;
+          (void)down;
+        }
         break;
       case SK_UP2:
         if (fwd_pack) s.fwd_off = add_pack(0, ident);
@@ -764,7 +789,9 @@ struct Engine {
           ++k;
         }
         if (!dry) {
-          const int launches = (op.kind == CK_DOWN4) ? 4 : 1;
+          const bool down_halo = op.kind == CK_DOWN4 && o.C % 64 == 0 && ng == 1 && grad_ch == cin_total;
+          REFID_REQUIRE(op.kind != CK_DOWN4 || down_halo, "down conv %s: unsupported channel count for the data-gradient", s.key.c_str());
+          const int launches = 1;
           for (int par = 0; par < launches; ++par) {
             ConvDesc d;
             memset(&d, 0, sizeof(d));
@@ -776,11 +803,10 @@ struct Engine {
             d.w = wpackb + s.dgrad_off;
             d.w_cols = cout;
             if (op.kind == CK_DOWN4) {
-              d.kind = CK_DOWN4_DGRAD;
-              d.parity = par;
-              d.w_rows = 16L * cin_total;
-              d.wrows_per_tap = cin_total;
-              d.w_row0 = par * 4 * cin_total + w_row0;
+              d.kind = CK_DOWN4_DGRAD_HALO;
+              d.w_rows = 36L * cin_total;
+              d.wrows_per_tap = 4 * cin_total;
+              d.w_row0 = w_row0;
             } else if (op.kind == CK_UP2) {
               d.kind = CK_UP2_DGRAD;
               d.w_rows = 4L * cin_total;

@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           }
           ++ia;
           if (!p.resident_b) {
+            const unsigned tmask = p.tap_mask[nblk] ? p.tap_mask[nblk] : 0xFFFFu;
             for (int tap = 0; tap < TAPS; ++tap) {
+              if (!((tmask >> tap) & 1u)) continue;
               const int sb = ib % SB;
               mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1, 0x710 + sb);
               if (elect_one()) {
@@ -268,6 +270,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     uint32_t ia = 0, ib = 0, it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
+      const unsigned tmask = p.tap_mask[item % p.n_blocks] ? p.tap_mask[item % p.n_blocks] : 0xFFFFu;
+      bool first = true;  // the first MMA of the item overwrites the accumulator
       mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x730 + buf);
       tc_fence_after();
       const uint32_t acc = tm + buf * ACC_COLS;
@@ -300,6 +304,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         } else {
 #pragma unroll 1
           for (int tap = 0; tap < TAPS; ++tap) {
+            if (!((tmask >> tap) & 1u)) continue;
             const int sb = ib % SB;
             mbar_wait(&b_full[sb], (ib / SB) & 1, 0x750 + sb);
             tc_fence_after();
@@ -313,15 +318,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
                 for (int k = 0; k < KSTEPS; ++k) {
                   const uint64_t ad = a_desc + (uint64_t)(((uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
                   const uint64_t bd = b_desc + (uint64_t)(((uint32_t)k * 32u) >> 4);
-                  umma_bf16(acc + j * BN, ad, bd, IDESC, (ks > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  umma_bf16(acc + j * BN, ad, bd, IDESC, (!first || k > 0) ? 1u : 0u);
                 }
               }
               umma_commit(&b_empty[sb]);
-              if (tap == TAPS - 1) umma_commit(&a_empty[sa]);
             }
             __syncwarp();
+            first = false;
             ++ib;
           }
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
         }
         ++ia;
       }
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         const int ch = nblk * BN + c0;
         e = &p.epi[ch >> p.epi_shift];
         cseg = ch & epi_mask;
-        const size_t pix = ((size_t)n * e->OH + (size_t)y) * e->OW + (size_t)x;
+        const size_t pix = ((size_t)n * e->OH + (size_t)(y * e->osy + e->ooy)) * e->OW + (size_t)(x * e->osx + e->oox);
         off = pix * (size_t)e->C + e->coff + cseg;
       };
       EpiPF cur, nxt;

@@ -54,3 +54,19 @@ def unpack_wgrad_conv(d, cout, cin, kh, kw):
 def unpack_wgrad_up2(d, cin, cout):
     """wgrad output D[(a*2+b)*Cout + co][ci] -> ConvTranspose2d weight gradient (Cin,Cout,2,2)."""
     return d.view(2, 2, cout, cin).permute(3, 2, 0, 1).contiguous()
+
+
+def pack_down_dgrad_halo(w):
+    """Data-gradient of the 4x4 stride-2 pad-1 conv on the halo-conv engine (csrc/convop.cuh CK_DOWN4_DGRAD_HALO):
+    rows = (tap9*4 + q)*Cin + ci, cols = co, where tap9 = (dy+1)*3 + (dx+1) indexes the 3x3 neighbourhood of dY and
+    q = qy*2+qx the parity of the dX pixel (2i+qy, 2j+qx); value = W[co,ci,ky,kx] with ky = qy + 1 - 2*dy, kx = qx + 1 - 2*dx
+    when inside the kernel, else 0."""
+    co, ci, _, _ = w.shape
+    out = torch.zeros(9, 4, ci, co, dtype=w.dtype, device=w.device)
+    for t9 in range(9):
+        dy, dx = t9 // 3 - 1, t9 % 3 - 1
+        for q in range(4):
+            ky, kx = (q >> 1) + 1 - 2 * dy, (q & 1) + 1 - 2 * dx
+            if 0 <= ky < 4 and 0 <= kx < 4:
+                out[t9, q] = w[:, :, ky, kx].t()
+    return out.reshape(36 * ci, co).contiguous()

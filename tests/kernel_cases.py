@@ -7,6 +7,7 @@ import torch.nn.functional as F
 from refid_b200 import _lib, packing
 
 CK_3X3, CK_1X1, CK_DOWN4, CK_UP2, CK_DOWN4_DGRAD, CK_UP2_DGRAD = range(6)
+CK_DOWN4_DGRAD_HALO = 7
 ACT_NONE, ACT_LRELU, ACT_GELU = 0, 1, 2
 
 
@@ -146,6 +147,20 @@ def case_down4_dgrad(N=2, H=8, W=8, c=64):
     return _err(nchw(out), ref)
 
 
+def case_down4_dgrad_halo(N=2, H=8, W=8, c=64, masked=True):
+    """All four output parities in one halo-conv launch (tap masks + stride-2 scatter), accumulate + LeakyReLU mask."""
+    gy = rb(g(N, c, H, W, seed=1))
+    w = rb(g(c, c, 4, 4, seed=2) / (4 * c ** 0.5))
+    sv = rb(g(N, c, 2 * H, 2 * W, seed=5))
+    ref = F.conv_transpose2d(gy, w, stride=2, padding=1)
+    if masked:
+        ref = ref * torch.where(sv > 0, 1.0, 0.2)
+    wp = packing.pack_down_dgrad_halo(w).to(torch.bfloat16)
+    o = run_conv(CK_DOWN4_DGRAD_HALO, [nhwc(gy)], wp, 4 * c, c, (N, 2 * H, 2 * W), sv=nhwc(sv) if masked else None,
+                 act=ACT_LRELU if masked else 0, slope=0.2)
+    return _err(nchw(o["out"]), ref)
+
+
 def case_up2_dgrad(N=2, H=16, W=16, cin=128, cout=64):
     """dgrad of ConvTranspose(cin->cout): dIn = conv2x2s2(dOut)."""
     go = rb(g(N, cout, H, W, seed=1))
@@ -210,6 +225,9 @@ CASES = {
     "up2_128_64": lambda: case_up2(),
     "up2_64_32": lambda: case_up2(cin=64, cout=32),
     "down4_dgrad_64": lambda: case_down4_dgrad(),
+    "down4_dgrad_halo_64": lambda: case_down4_dgrad_halo(),
+    "down4_dgrad_halo_128_ragged": lambda: case_down4_dgrad_halo(c=128, H=20, W=12, N=3),
+    "down4_dgrad_halo_256": lambda: case_down4_dgrad_halo(c=256, H=8, W=8, N=1, masked=False),
     "up2_dgrad_128_64": lambda: case_up2_dgrad(),
     "wgrad3x3_64_64": lambda: case_wgrad3x3(),
     "wgrad3x3_dual_64+64_64": lambda: case_wgrad3x3(cin2=64),
