@@ -193,6 +193,18 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
   f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
   f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
 }
+// 256-bit global accesses (sm_100: LDG/STG.256): a thread's 32 B chunk in ONE instruction -- half the L1 wavefronts of two
+// 128-bit accesses when every lane touches a different 128-byte line (pixel-per-lane epilogues).  32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
   uint4 a;
   a.x = pack_bf16(f[0], f[1]); a.y = pack_bf16(f[2], f[3]); a.z = pack_bf16(f[4], f[5]); a.w = pack_bf16(f[6], f[7]);

@@ -88,6 +88,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   const bool down_dgrad = d.kind == CK_DOWN4_DGRAD_HALO;
   if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad) return 0;
   if (down_dgrad && ngroups != 1) return 0;
+  for (int g = 0; g < ngroups; ++g)  // GELU epilogues exist on the halo engine for 1x1 convs only (EGACA); else tap-GEMM
+    if (groups[g].epi.act == ACT_GELU && d.kind != CK_1X1) return 0;
   static const int disabled = getenv("REFID_NO_HALO") ? 1 : 0;
   if (disabled) return 0;
   int ktot = 0, kc = 64;
@@ -118,6 +120,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.w_row0 = d.w_row0;
   h.nsrc = d.nsrc;
   h.kc = kc;
+  static const int dbg = getenv("REFID_HALO_DBG") ? atoi(getenv("REFID_HALO_DBG")) : 0;
+  h.dbg = dbg;
   for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / kc;
   h.n_blocks = (down_dgrad ? 4 : 1) * (total / BN);
   if (h.n_blocks > kMaxNBlocks || (down_dgrad && 4 * (total / seg) > kMaxNBlocks)) return 0;

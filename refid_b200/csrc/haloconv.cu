@@ -22,20 +22,17 @@ struct EpiPF {
 __device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, bool valid, EpiPF& f) {
   if (!valid) return;
   if (e.pre) {
-    const uint4* q = reinterpret_cast<const uint4*>(e.pre + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) f.a[i] = q[i];
+    ldg256(e.pre + off, f.a[0], f.a[1]);
+    ldg256(e.pre + off + 16, f.a[2], f.a[3]);
   }
   if (e.pre2) {
-    const uint4* q = reinterpret_cast<const uint4*>(e.pre2 + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) f.b[i] = q[i];
+    ldg256(e.pre2 + off, f.b[0], f.b[1]);
+    ldg256(e.pre2 + off + 16, f.b[2], f.b[3]);
   }
   const __nv_bfloat16* third = e.sv ? e.sv : e.post;
   if (third) {
-    const uint4* q = reinterpret_cast<const uint4*>(third + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) f.c[i] = q[i];
+    ldg256(third + off, f.c[0], f.c[1]);
+    ldg256(third + off + 16, f.c[2], f.c[3]);
   }
 }
 
@@ -58,20 +55,23 @@ __device__ __forceinline__ void unpack32(const uint4* q, float* f) {
   }
 }
 __device__ __forceinline__ void store32(__nv_bfloat16* ptr, const float* v) {
-  uint4* o = reinterpret_cast<uint4*>(ptr);
+  uint4 t[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    uint4 t;
-    t.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-    t.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-    t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-    t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-    o[i] = t;
+    t[i].x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    t[i].y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    t[i].z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    t[i].w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
   }
+  stg256(ptr, t[0], t[1]);
+  stg256(ptr + 16, t[2], t[3]);
 }
 
 // Epilogue of 32 consecutive output channels of one pixel (same arithmetic as epi_apply16 in tapgemm.cu; see EpiDesc),
 // global operands taken from the prefetched registers.  `off` = element offset of channel 0 of the group.
+// GELU (exact erf: ~60 instructions per element, twice) is compiled only into the GELU instantiations: inlined into every
+// kernel it made the epilogue's hot path hop over tens of KB of cold code and miss the instruction cache.
+template <bool GELU>
 __device__ __forceinline__ void epi_apply32_pf(const EpiDesc& e, float* v, size_t off, int cseg, int n, int y, int x,
                                                const EpiPF& f) {
   if (e.bias) {
@@ -97,7 +97,7 @@ __device__ __forceinline__ void epi_apply32_pf(const EpiDesc& e, float* v, size_
   if (e.sv) {
     float t[32];
     unpack32(f.c, t);
-    if (e.act == ACT_GELU) {
+    if (GELU && e.act == ACT_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(t[i]);
     } else {
@@ -111,7 +111,7 @@ __device__ __forceinline__ void epi_apply32_pf(const EpiDesc& e, float* v, size_
       const float sl = e.slope;
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
-    } else if (e.act == ACT_GELU) {
+    } else if (GELU && e.act == ACT_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
     }
@@ -153,7 +153,7 @@ __device__ __forceinline__ void epi_apply32_pf(const EpiDesc& e, float* v, size_
 // so the single issuing thread has <= 62 cycles per MMA at N <= 128.  The producer and MMA warps therefore run their
 // loops warp-uniformly (warp index via shuffle, elect.sync only around the issue) so that descriptors live in uniform
 // registers, and every per-MMA descriptor is `base + compile-time constant` (TAPS / pitch / NM are template parameters).
-template <int BN, int NM, int TAPS, int KC>
+template <int BN, int NM, int TAPS, int KC, bool GELU>
 __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PITCH = TAPS == 9 ? 10 : 8;       // pixels per patch row in shared memory
@@ -364,6 +364,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         off = pix * (size_t)e->C + e->coff + cseg;
       };
       EpiPF cur, nxt;
+      if (p.dbg == 1 || p.dbg == 2) {
+        mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
+        tc_fence_after();
+        if (p.dbg == 1) {
+          for (int g = hsel; g < G; g += 2) {
+            float v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)((g / GPT) * BN + (g % GPT) * 32);
+            tmem_ld16(taddr, v);
+            tmem_ld16(taddr + 16, v + 16);
+            tmem_ld_wait();
+            if (v[0] == 123.456f) p.epi[0].out[0] = __float2bfloat16(v[5]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
       if (hsel < G) {
         const EpiDesc* e;
         size_t off;
@@ -391,7 +409,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         tmem_ld16(taddr, v);
         tmem_ld16(taddr + 16, v + 16);
         tmem_ld_wait();
-        if (valid) epi_apply32_pf(*e, v, off, cseg, n, y, x, cur);
+        if (p.dbg >= 3) {  // diagnostics: 3 = no stores, 4 = no bias loads, 5 = neither
+          EpiDesc ee = *e;
+          if (p.dbg == 3 || p.dbg == 5) ee.out = nullptr, ee.out2 = nullptr;
+          if (p.dbg == 4 || p.dbg == 5) ee.bias = nullptr;
+          if (valid) epi_apply32_pf<GELU>(ee, v, off, cseg, n, y, x, cur);
+          if (v[3] == 123.456f) p.epi[0].out[0] = __float2bfloat16(v[5]);
+        } else if (valid) epi_apply32_pf<GELU>(*e, v, off, cseg, n, y, x, cur);
         cur = nxt;
       }
       tc_fence_before();
@@ -418,11 +442,11 @@ size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
   return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + 1024;
 }
 
-template <int BN, int NM, int TAPS, int KC>
+template <int BN, int NM, int TAPS, int KC, bool GELU>
 int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC, GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
     configured = true;
   }
   static int num_sms = 0;
@@ -432,7 +456,7 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
     REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  haloconv_kernel<BN, NM, TAPS, KC><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
+  haloconv_kernel<BN, NM, TAPS, KC, GELU><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -468,12 +492,17 @@ int haloconv_plan(HaloConvParams* p, int BN, int NM) {
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream) {
   REFID_REQUIRE((p.num_taps == 9 && p.halo == 1 && p.pitch_px == 10) || (p.num_taps == 1 && p.halo == 0 && p.pitch_px == 8),
                 "haloconv: taps/halo/pitch %d/%d/%d unsupported", p.num_taps, p.halo, p.pitch_px);
+  bool gelu = false;
+  for (int i = 0; i < kMaxNBlocks; ++i) gelu = gelu || p.epi[i].act == ACT_GELU;
+  REFID_REQUIRE(!gelu || (p.num_taps == 1 && p.kc == 64), "haloconv: GELU epilogues are instantiated for 1x1 / 64-channel slabs only");
 #define HINST(bn, nm)                                                                                        \
-  if (BN == bn && NM == nm && p.kc == 64)                                                                   \
-    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9, 64>(p, stream) : launch_halo_inst<bn, nm, 1, 64>(p, stream);
+  if (BN == bn && NM == nm && p.kc == 64) {                                                                 \
+    if (p.num_taps == 9) return launch_halo_inst<bn, nm, 9, 64, false>(p, stream);                          \
+    return gelu ? launch_halo_inst<bn, nm, 1, 64, true>(p, stream) : launch_halo_inst<bn, nm, 1, 64, false>(p, stream); \
+  }
 #define HINST32(bn, nm)                                                                                      \
   if (BN == bn && NM == nm && p.kc == 32)                                                                   \
-    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9, 32>(p, stream) : launch_halo_inst<bn, nm, 1, 32>(p, stream);
+    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9, 32, false>(p, stream) : launch_halo_inst<bn, nm, 1, 32, false>(p, stream);
   HINST(32, 1) HINST(64, 1) HINST(128, 1) HINST(256, 1)
   HINST(32, 2) HINST(64, 2) HINST(128, 2)
   HINST32(32, 1) HINST32(64, 1) HINST32(128, 1)

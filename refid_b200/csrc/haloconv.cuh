@@ -23,6 +23,7 @@ struct HaloConvParams {
   int epi_seg;      // output channels per EpiDesc (power of two, divides BN)
   int epi_shift;    // log2(epi_seg)
   unsigned short tap_mask[kMaxNBlocks];  // per N block: taps to execute (0 = all); streamed-weight path only
+  int dbg;          // diagnostics (REFID_HALO_DBG): 1 = epilogue does no global memory work, 2 = no TMEM reads either
   int kc;           // channels per K slab: 64 (128B-swizzled pixel rows) or 32 (64B)
   int num_taps;     // 9 or 1
   int halo;         // 1 (3x3) or 0 (1x1)

@@ -1,0 +1,43 @@
+"""Single-kernel timing of halo-conv shapes through the C ABI (diagnostic). Usage: python tools/conv_bench.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import torch
+import kernel_cases as K
+from refid_b200 import packing, _lib
+import ctypes
+
+def bench(cin, cout, H, W, N, cin2=0, pre=False, reps=20):
+    x = K.rb(K.g(N, cin + cin2, H, W, seed=1))
+    w = K.rb(K.g(cout, cin + cin2, 3, 3, seed=2) / (3 * (cin + cin2) ** 0.5))
+    b = K.g(cout, seed=3) * 0.1
+    ins = [K.nhwc(x[:, :cin])] + ([K.nhwc(x[:, cin:])] if cin2 else [])
+    wp = packing.pack_fwd(w).to(torch.bfloat16)
+    r = K.nhwc(K.rb(K.g(N, cout, H, W, seed=4))) if pre else None
+    out = torch.empty(N, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    L = _lib.lib()
+    def run():
+        rc = L.refid_test_conv(K.CK_3X3, 0, _lib.ptr(ins[0]), cin, _lib.ptr(ins[1] if cin2 else None), cin2, N, H, W, _lib.ptr(wp),
+                               ctypes.c_long(wp.shape[0]), wp.shape[1], cout, 0, cout, _lib.ptr(b), _lib.ptr(r), None, K.ACT_LRELU,
+                               ctypes.c_float(0.1), _lib.ptr(out), None, None, None, None, None)
+        _lib.check(rc, "conv")
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): run()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    fl = 2.0 * N * H * W * 9 * (cin + cin2) * cout
+    print(f"cin {cin}+{cin2} cout {cout} {N}x{H}x{W} pre={pre}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF/s  (includes per-call TMA map encode on host)", flush=True)
+
+print("REFID_HALO_DBG =", os.environ.get("REFID_HALO_DBG"))
+bench(64, 64, 256, 256, 8)
+bench(64, 64, 256, 256, 8, pre=True)
+if os.environ.get("REFID_HALO_DBG", "0") == "0":
+    bench(64, 64, 256, 256, 8, cin2=64)
+    bench(128, 128, 128, 128, 8)
+    bench(128, 128, 128, 128, 8, cin2=128)
+    bench(256, 256, 64, 64, 8)
+    bench(256, 256, 64, 64, 8, cin2=256)
+    bench(32, 32, 256, 256, 8)

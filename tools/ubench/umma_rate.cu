@@ -4,7 +4,7 @@
 #include "../../refid_b200/csrc/common.cu"
 using namespace refid;
 
-__global__ void __launch_bounds__(128, 1) k_rate(int M, int N, int iters, int a_stride, int b_stride, long long* out) {
+__global__ void __launch_bounds__(128, 1) k_rate(int M, int N, int iters, int a_stride, int b_stride, long long* out, int a_off, int a_sbo) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128, 1) k_rate(int M, int N, int iters, int a_
       const uint32_t aa = a0 + (uint32_t)((it & 3) * a_stride), bb = b0 + (uint32_t)((it & 3) * b_stride);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        umma_bf16(tm + (uint32_t)((it & 1) * N), make_smem_desc(aa + k * 32, 16, 1024, 2), make_smem_desc(bb + k * 32, 16, 1024, 2), idesc, 1);
+        umma_bf16(tm + (uint32_t)((it & 1) * N), make_smem_desc(aa + a_off + k * 32, 16, a_sbo, 2), make_smem_desc(bb + k * 32, 16, 1024, 2), idesc, 1);
       }
     }
     umma_commit(&bar);
@@ -42,7 +42,7 @@ int main() {
   int Ms[] = {128, 64}; int Ns[] = {32, 64, 96, 128, 192, 256};
   for (int M : Ms) for (int N : Ns) {
     const int iters = 2000;
-    k_rate<<<148, 128, 201 * 1024 + 1024>>>(M, N, iters, 16384, 16384, d);
+    k_rate<<<148, 128, 201 * 1024 + 1024>>>(M, N, iters, 16384, 16384, d, 0, 1024);
     cudaError_t e = cudaGetLastError(); cudaError_t e2 = cudaDeviceSynchronize(); if (e == cudaSuccess) e = e2;
     long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
@@ -50,6 +50,16 @@ int main() {
     double ideal = (M < 128 ? 128 : M) * (double)N / 256.0;
     printf("M=%3d N=%3d: %.1f cyc/MMA (floor %.0f) eff %.2f  flop/clk/SM %.0f  %s\n", M, N, cyc, ideal, ideal * (M / 128.0) / cyc * (M<128?1:1),
            2.0 * M * N * 16 / cyc, cudaGetErrorString(e));
+  }
+  printf("--- A operand start offset / SBO variants (M=128) ---\n");
+  int offs[] = {0, 128, 256, 512, 1152}; int sbos[] = {1024, 1280, 1152};
+  for (int N : {64, 128, 256}) for (int sbo : sbos) for (int off : offs) {
+    const int iters = 2000;
+    k_rate<<<148, 128, 201 * 1024 + 1024>>>(128, N, iters, 24576, 16384, d, off, sbo);
+    cudaError_t e = cudaGetLastError(); cudaError_t e2 = cudaDeviceSynchronize(); if (e == cudaSuccess) e = e2;
+    long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("N=%3d sbo=%4d a_off=%4d: %.1f cyc/MMA  %s\n", N, sbo, off, (double)mx / (iters * 4), cudaGetErrorString(e));
   }
   return 0;
 }
