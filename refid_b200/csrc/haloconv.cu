@@ -598,12 +598,12 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int haloconv_plan(HaloConvParams* p, int BN, int NM) {
+int haloconv_plan(HaloConvParams* p, int BN, int NM, int mode) {
   if (2 * NM * BN > 512) return 0;
   p->patch_rows = 16 * NM + 2 * p->halo;
   const int total_slabs = p->src_slabs[0] + (p->nsrc > 1 ? p->src_slabs[1] : 0);
   // weights resident for the whole kernel when they fit next to >= 2 activation stages
-  if (p->n_blocks == 1) {
+  if (p->n_blocks == 1 && mode != 2) {
     p->resident_b = 1;
     p->stages_b = 0;
     for (int sa = total_slabs >= 3 ? 3 : 2; sa >= 2; --sa) {
@@ -611,6 +611,7 @@ int haloconv_plan(HaloConvParams* p, int BN, int NM) {
       if (halo_smem_bytes(*p, BN) <= kHaloSmemMax) return 1;
     }
   }
+  if (mode == 1) return 0;
   p->resident_b = 0;
   p->stages_a = 2;
   for (int sb = kHaloMaxStages; sb >= 3; --sb) {

@@ -41,7 +41,8 @@ struct HaloConvParams {
 };
 
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);
-// Shared-memory plan; returns 0 when the configuration does not fit.
-int haloconv_plan(HaloConvParams* p, int BN, int NM);
+// Shared-memory plan; returns 0 when the configuration does not fit.  mode 0: resident weights if they fit, else
+// streamed; 1: resident only; 2: streamed only.
+int haloconv_plan(HaloConvParams* p, int BN, int NM, int mode = 0);
 
 }  // namespace refid
