@@ -332,6 +332,7 @@ static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLa
   memset(&h, 0, sizeof(h));
   h.mode = mode;
   h.out = outp;
+  h.bias_out = d.bias_grad;
   h.CQ = q.C;
   h.cp_total = cp_total;
   h.nsrc = d.nsrc;
@@ -358,6 +359,7 @@ static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLa
     if (make_act_map(&h.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, 64, 10, rows, 1)) return -1;
   if (make_act_map(&h.tmQ, q.ptr, d.N, d.H, d.W, q.pitch, q.C, 0, 0, 1, 64, 8, 16, 1)) return -1;
   l->use_halo = 1;
+  l->bias_done = d.bias_grad != nullptr;
   return 1;
 }
 
@@ -365,6 +367,7 @@ int build_wgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
   TapTable tt;
   if (fill_taps(d.kind, d.parity, &tt)) return 1;
   l->use_halo = 0;
+  l->bias_done = 0;
   {
     const int r = try_build_halowgrad(d, q, outp, l);
     if (r < 0) return 1;

@@ -43,6 +43,7 @@ struct EmapArena {
 
 struct ConvDesc {
   EmapArena* arena;  // nullptr: direct (non-staged) epilogue only
+  float* bias_grad;  // build_wgrad only: fp32 [Cout] bias-gradient accumulator the launch may fill (see WgradLaunch::bias_done)
   int kind;
   int parity;  // CK_DOWN4_DGRAD only: output parity py*2+px
   ActSrc src[2];
@@ -74,6 +75,7 @@ struct WgradLaunch {
   WgradParams p;
   int pixel_chunks;
   int use_halo;  // stride-1 3x3 with 64-channel-multiple operands runs on the halo-wgrad kernel
+  int bias_done; // the launch also accumulates the bias gradient (ConvDesc::bias_grad)
   HaloWgradParams hp;
 };
 // d describes the tapped operand P (kind, sources, taps); q is the un-shifted operand on the op's output grid.

@@ -1485,10 +1485,10 @@ struct Engine {
       const Series& sr = series[o.series];
       const __nv_bfloat16* gz = P(sr.gbase + (long)o.slot * (long)sr.slot_bytes);
       cur_label = s.key;
-      if (s.b_off >= 0) emit_colsum(gz, (long)n * o.N * o.H * o.W, o.C, gflat + s.b_off);
       if (dry) continue;
       ConvDesc d;
       memset(&d, 0, sizeof(d));
+      d.bias_grad = s.b_off >= 0 ? gflat + s.b_off : nullptr;
       ActSrc q;
       if (op.kind == CK_UP2) {
         d.kind = CK_UP2_DGRAD;
@@ -1512,6 +1512,7 @@ struct Engine {
       }
       WgradLaunch wl;
       if (build_wgrad(d, q, gflat + s.w_off, &wl)) return 1;
+      if (s.b_off >= 0 && !wl.bias_done) emit_colsum(gz, (long)n * o.N * o.H * o.W, o.C, gflat + s.b_off);
       emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, conv_flops(op) * n, ":wgrad");
     }
     cur_label = "";

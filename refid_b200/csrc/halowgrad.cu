@@ -83,10 +83,12 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
   const int src = slab >= p.src_slabs[0] ? 1 : 0;
   const int slab_in_src = slab - (src ? p.src_slabs[0] : 0);
 
+  // bias gradient: one job per Cout block also column-sums the G tiles it streams (4 extra arrivals free a stage)
+  const bool colsum = p.bias_out != nullptr && (MODE == 64 ? job == 0 : (slab == 0 && dy == -1));
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHWMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], colsum ? 5 : 1);
     }
     mbar_init(acc_bar, 1);
     fence_barrier_init();
@@ -177,6 +179,51 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
       // ---------------- epilogue: TMEM -> fp32 global reductions, once per CTA ----------------
       const int q = warp & 3;
       const int m = q * 32 + lane;  // accumulator row
+      if (colsum) {
+        // thread m sums pixel row m (MODE 64) or rows (m & 63), (m & 63) + 64 of its 64-channel half (MODE 128)
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        const uint32_t smem_u = smem_u32(smem);
+        int it = 0;
+        for (int t = t_begin; t < t_end; ++t, ++it) {
+          const int s = it % S;
+          mbar_wait(&full_bar[s], (it / S) & 1, 0x830 + s);
+          const uint32_t gt = smem_u + (uint32_t)s * Cfg::STAGE + Cfg::P_ALLOC + (MODE == 128 ? (uint32_t)(m >> 6) * 16384u : 0u);
+#pragma unroll
+          for (int rr = 0; rr < (MODE == 128 ? 2 : 1); ++rr) {
+            const int row = MODE == 128 ? (m & 63) + rr * 64 : m;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              uint4 u;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                           : "r"(gt + (uint32_t)row * 128u + (uint32_t)((k ^ (row & 7)) << 4)));
+              acc[8 * k + 0] += bf16_lo(u.x); acc[8 * k + 1] += bf16_hi(u.x);
+              acc[8 * k + 2] += bf16_lo(u.y); acc[8 * k + 3] += bf16_hi(u.y);
+              acc[8 * k + 4] += bf16_lo(u.z); acc[8 * k + 5] += bf16_hi(u.z);
+              acc[8 * k + 6] += bf16_lo(u.w); acc[8 * k + 7] += bf16_hi(u.w);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        // all lanes of a warp hold the same channels (and in MODE 128 the same half): reduce over lanes, one atomic per channel
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          float v = acc[i];
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          acc[i] = v;
+        }
+        if (lane == 0) {
+          float* bo = p.bias_out + (MODE == 128 ? coblk * 128 + (m >> 6) * 64 : 0);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) atomicAdd(bo + i, acc[i]);
+        }
+      }
       mbar_wait(acc_bar, 0, 0x820);
       tc_fence_after();
 #pragma unroll 1
