@@ -259,7 +259,7 @@ def main():
             cn = sum(v["launches"] for v in conv.values())
             tot = sum(v["ms"] for v in prof.values())
             ach = cfl / (cms * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "tapgemm_kernel (conv forward + data-gradient tap-GEMM, tcgen05)",
+            line["roofline"] = {"bound": "tensor", "kernel": "haloconv_kernel / tapgemm_kernel (conv forward + data-gradient implicit GEMM, tcgen05)",
                                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                                 "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                                 "traffic": None, "launches_per_step": cn, "avg_launch_ms": cms / max(cn, 1),

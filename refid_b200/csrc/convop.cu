@@ -106,7 +106,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     int c = groups[g].channels & -groups[g].channels;  // largest power of two dividing the group
     if (c < seg) seg = c;
   }
-  int BN = kc == 64 ? 256 : 128;
+  static const int bn_max = getenv("REFID_HALO_BNMAX") ? atoi(getenv("REFID_HALO_BNMAX")) : 256;
+  int BN = kc == 64 ? bn_max : 128;
   while (BN > 32 && total % BN) BN >>= 1;
   if (total % BN) return 0;
   if (seg > BN) seg = BN;

@@ -255,19 +255,23 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __re
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = sw[64 * 9 + grp * 8 + k];
+    // nine unconditional loads (clamped address, zero weight outside the image) issued together, then the arithmetic
+    uint4 ra[9];
+    float ma[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= H) continue;
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      ma[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? 1.f : 0.f;
+      const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
+      ra[t] = *reinterpret_cast<const uint4*>(a + (((size_t)n * H + yc) * W + xc) * 64 + grp * 8);
+    }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= W) continue;
-        float v[8];
-        load8(a + (((size_t)n * H + yy) * W + xx) * 64 + grp * 8, v);
+    for (int t = 0; t < 9; ++t) {
+      float v[8];
+      v[0] = bf16_lo(ra[t].x); v[1] = bf16_hi(ra[t].x); v[2] = bf16_lo(ra[t].y); v[3] = bf16_hi(ra[t].y);
+      v[4] = bf16_lo(ra[t].z); v[5] = bf16_hi(ra[t].z); v[6] = bf16_lo(ra[t].w); v[7] = bf16_hi(ra[t].w);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k] * sw[(grp * 8 + k) * 9 + ky * 3 + kx];
-      }
+      for (int k = 0; k < 8; ++k) acc[k] += ma[t] * v[k] * sw[(grp * 8 + k) * 9 + t];
     }
     store8(d + (size_t)pix * 64 + grp * 8, acc);
 #pragma unroll
@@ -327,32 +331,45 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __re
     if (pix >= npix) break;
     const int n = (int)(pix / hw);
     const int y = (int)((pix % hw) / W), x = (int)(pix % W);
-    float gc[8];
-    load8(gd + (size_t)pix * 64 + grp * 8, gc);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) ab[k] += gc[k];
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // All 18 neighbour chunks are fetched unconditionally (clamped address, zero weight outside the image) and BEFORE any
+    // use, so the loads are in flight together; with a branch around every load they were issued one latency at a time.
+    uint4 ra[9], rg[9];
+    float ma[9], mg[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        // weight gradient: a[p + off] * gd[p]
-        const int yy = y + ky - 1, xx = x + kx - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          float v[8];
-          load8(a + (((size_t)n * H + yy) * W + xx) * 64 + grp * 8, v);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) aw[k][ky * 3 + kx] += v[k] * gc[k];
-        }
-        // data gradient: gd[p - off] * w[tap]
-        const int y2 = y - (ky - 1), x2 = x - (kx - 1);
-        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
-          float v[8];
-          load8(gd + (((size_t)n * H + y2) * W + x2) * 64 + grp * 8, v);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] += v[k] * sw[(grp * 8 + k) * 9 + ky * 3 + kx];
-        }
+        const int t = ky * 3 + kx;
+        const int yy = y + ky - 1, xx = x + kx - 1;      // weight gradient: a[p + off] * gd[p]
+        const int y2 = y - (ky - 1), x2 = x - (kx - 1);  // data gradient:   gd[p - off] * w[tap]
+        ma[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? 1.f : 0.f;
+        mg[t] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? 1.f : 0.f;
+        const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
+        const int y2c = min(max(y2, 0), H - 1), x2c = min(max(x2, 0), W - 1);
+        ra[t] = *reinterpret_cast<const uint4*>(a + (((size_t)n * H + yc) * W + xc) * 64 + grp * 8);
+        rg[t] = *reinterpret_cast<const uint4*>(gd + (((size_t)n * H + y2c) * W + x2c) * 64 + grp * 8);
       }
+    }
+    float gc[8];
+    {
+      const uint4 c = rg[4];  // centre tap = gd[p]
+      gc[0] = bf16_lo(c.x); gc[1] = bf16_hi(c.x); gc[2] = bf16_lo(c.y); gc[3] = bf16_hi(c.y);
+      gc[4] = bf16_lo(c.z); gc[5] = bf16_hi(c.z); gc[6] = bf16_lo(c.w); gc[7] = bf16_hi(c.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ab[k] += gc[k];
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float v[8];
+      v[0] = bf16_lo(ra[t].x); v[1] = bf16_hi(ra[t].x); v[2] = bf16_lo(ra[t].y); v[3] = bf16_hi(ra[t].y);
+      v[4] = bf16_lo(ra[t].z); v[5] = bf16_hi(ra[t].z); v[6] = bf16_lo(ra[t].w); v[7] = bf16_hi(ra[t].w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) aw[k][t] += ma[t] * v[k] * gc[k];
+      v[0] = bf16_lo(rg[t].x); v[1] = bf16_hi(rg[t].x); v[2] = bf16_lo(rg[t].y); v[3] = bf16_hi(rg[t].y);
+      v[4] = bf16_lo(rg[t].z); v[5] = bf16_hi(rg[t].z); v[6] = bf16_lo(rg[t].w); v[7] = bf16_hi(rg[t].w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += mg[t] * v[k] * sw[(grp * 8 + k) * 9 + t];
     }
     store8(ga + (size_t)pix * 64 + grp * 8, acc);
   }
