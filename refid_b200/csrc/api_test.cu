@@ -52,17 +52,8 @@ int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* i
     g[1].epi.bias = bias ? bias + cg : nullptr;
     ng = 2;
   }
-  // staged-epilogue tensor maps live in device memory: a small static arena, refilled per call (tests are synchronous)
-  static CUtensorMap* dev_maps = nullptr;
-  static std::vector<CUtensorMap> host_maps;
-  if (!dev_maps) REFID_CUDA_CHECK(cudaMalloc(&dev_maps, 256 * sizeof(CUtensorMap)));
-  host_maps.clear();
-  EmapArena arena{&host_maps, dev_maps, 256};
-  d.arena = &arena;
   TapGemmLaunch l;
   if (build_conv(d, g, ng, &l)) return 1;
-  if (!host_maps.empty())
-    REFID_CUDA_CHECK(cudaMemcpy(dev_maps, host_maps.data(), host_maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   return run_conv(l, static_cast<cudaStream_t>(stream));
 }
 

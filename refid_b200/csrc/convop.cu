@@ -144,36 +144,20 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.N = d.N;
   h.H = d.H;
   h.W = d.W;
-  // staged (TMA) epilogue: plain bf16 tiles only; the fp32 / NCHW / pre-activation / scattered outputs stay direct
-  // Opt-in (REFID_TMA_EPI=1): measured on B200 the staged variant (4 warps, two proxy fences + one bulk-group wait per
-  // 32-channel group) is slower than the direct 8-warp epilogue with 256-bit accesses (64->64 3x3, B=8, 256^2: 68 vs 51 us).
-  static const int tma_epi = getenv("REFID_TMA_EPI") ? 1 : 0;
-  bool staged = d.arena != nullptr && !down_dgrad && tma_epi;
-  int n_ein = 0, n_eout = 0, n_desc = 0;
+  int n_ein = 0;
   for (int g = 0; g < ngroups; ++g) {
     const EpiDesc& e = groups[g].epi;
-    if (e.out_f32 || e.out_nchw || e.out_pre || (!e.out && !e.out2)) staged = false;
-    const int ni = (e.pre ? 1 : 0) + (e.pre2 ? 1 : 0) + ((e.sv || e.post) ? 1 : 0), no = (e.out ? 1 : 0) + (e.out2 ? 1 : 0);
-    n_ein = ni > n_ein ? ni : n_ein;
-    n_eout = no > n_eout ? no : n_eout;
-    n_desc += groups[g].channels / seg;
+    n_ein += (e.pre ? 1 : 0) + (e.pre2 ? 1 : 0) + ((e.sv || e.post) ? 1 : 0);
   }
-  if (staged && d.arena->host->size() + 5 * (size_t)n_desc > d.arena->capacity) staged = false;
-  h.epi_tma = staged ? 1 : 0;
-  h.n_ein = n_ein;
-  h.n_eout = n_eout;
+  h.epi_inputs = n_ein > 0;
   // preference: resident weights (two pixel tiles per item, else one) before streamed weights -- re-streaming the
   // weights of a C=64 dual-source conv per 256-pixel item costs more than the smaller M (measured 111 vs 83 us MMA-side)
   const int nm_pref = (2 * 2 * BN <= 512 && d.H > 16) ? 2 : 1;
   int NM = 0;
-  for (int pass = 0; pass < 2 && !NM; ++pass) {
-    if (haloconv_plan(&h, BN, nm_pref, 1)) NM = nm_pref;
-    else if (haloconv_plan(&h, BN, 1, 1)) NM = 1;
-    else if (haloconv_plan(&h, BN, nm_pref, 2)) NM = nm_pref;
-    else if (haloconv_plan(&h, BN, 1, 2)) NM = 1;
-    else if (h.epi_tma) h.epi_tma = 0;  // no room for the staging tiles next to the operand stages: retry direct
-    else return 0;
-  }
+  if (haloconv_plan(&h, BN, nm_pref, 1)) NM = nm_pref;
+  else if (haloconv_plan(&h, BN, 1, 1)) NM = 1;
+  else if (haloconv_plan(&h, BN, nm_pref, 2)) NM = nm_pref;
+  else if (haloconv_plan(&h, BN, 1, 2)) NM = 1;
   if (!NM) return 0;
   h.tiles_x = (d.W + 7) / 8;
   h.tiles_y = (d.H + 16 * NM - 1) / (16 * NM);
@@ -194,21 +178,6 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
         e.OW = down_dgrad ? 2 * d.W : d.W;
         h.epi[nd++] = e;
       }
-  if (h.epi_tma) {
-    // 5 maps per EpiDesc: out, out2, pre, pre2, (sv | post); channel window = the descriptor's segment
-    std::vector<CUtensorMap>& hv = *d.arena->host;
-    h.emaps = d.arena->dev + hv.size();
-    for (int i = 0; i < nd; ++i) {
-      const EpiDesc& e = h.epi[i];
-      const __nv_bfloat16* ptrs[5] = {e.out, e.out2, e.pre, e.pre2, e.sv ? e.sv : e.post};
-      for (int k = 0; k < 5; ++k) {
-        CUtensorMap m;
-        memset(&m, 0, sizeof(m));
-        if (ptrs[k] && make_act_map(&m, ptrs[k] + e.coff, d.N, d.H, d.W, e.C, seg, 0, 0, 1, 32, 8, 4, 1)) return -1;
-        hv.push_back(m);
-      }
-    }
-  }
   out->use_halo = 1;
   out->BN = BN;
   out->BK = 64;

@@ -1,7 +1,5 @@
 // Host-side description of one convolution-shaped op and its lowering onto the tap-GEMM / wgrad kernels.
 #pragma once
-#include <vector>
-
 #include "haloconv.cuh"
 #include "halowgrad.cuh"
 #include "tapgemm.cuh"
@@ -33,16 +31,7 @@ struct OutGroup {
   EpiDesc epi;   // out/out2/pre/.../bias/act/slope/C/coff set by caller; geometry fields filled by the lowering
 };
 
-// Tensor maps that must live in DEVICE memory (the staged epilogue has too many for the kernel parameter space): the
-// builder appends to `host`; the owner copies `host` to `dev` (same indexing) before the first launch.
-struct EmapArena {
-  std::vector<CUtensorMap>* host;
-  const CUtensorMap* dev;
-  size_t capacity;  // maps
-};
-
 struct ConvDesc {
-  EmapArena* arena;  // nullptr: direct (non-staged) epilogue only
   float* bias_grad;  // build_wgrad only: fp32 [Cout] bias-gradient accumulator the launch may fill (see WgradLaunch::bias_done)
   int kind;
   int parity;  // CK_DOWN4_DGRAD only: output parity py*2+px

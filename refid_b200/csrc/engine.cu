@@ -102,7 +102,6 @@ struct LaunchMeta {
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-constexpr size_t kEmapBytes = 48u << 20;  // 393 216 tensor maps
 
 }  // namespace
 
@@ -133,8 +132,6 @@ struct Engine {
   std::vector<std::function<int()>> tape;
   std::vector<std::pair<size_t, size_t>> f32_zero;
   std::vector<int> release_after;  // pool buffers of pending addends consumed by the launch being built
-  std::vector<CUtensorMap> emap_host;  // staged-epilogue tensor maps; copied to the head of the workspace after planning
-  EmapArena arena = {nullptr, nullptr, 0};
   std::vector<Series> series;
   std::map<std::string, int> series_idx;
   int cur_slot = -1;       // slot of the per-step tensors being created (-1: outside the time sweeps)
@@ -627,7 +624,6 @@ struct Engine {
       cur_label = s.key;
       ConvDesc d;
       memset(&d, 0, sizeof(d));
-      d.arena = &arena;
       d.kind = op.kind;
       d.nsrc = op.nin;
       int cin_total = 0;
@@ -799,8 +795,7 @@ struct Engine {
           for (int par = 0; par < launches; ++par) {
             ConvDesc d;
             memset(&d, 0, sizeof(d));
-            d.arena = &arena;
-            d.src[0] = {gz, o.C, o.pitch};
+                  d.src[0] = {gz, o.C, o.pitch};
             d.nsrc = 1;
             d.N = o.N;
             d.H = o.H;
@@ -1398,7 +1393,6 @@ struct Engine {
       g.epi.C = t.pitch;
       ConvDesc d;
       memset(&d, 0, sizeof(d));
-      d.arena = &arena;
       d.kind = CK_1X1;
       d.src[0] = {sum, c, c, 0};
       d.nsrc = 1;
@@ -1549,11 +1543,7 @@ struct Engine {
     site_calls.clear();
     site_batched.clear();
     cur_slot = -1;
-    // the head of the workspace holds the device copy of the staged-epilogue tensor maps
-    emap_host.clear();
-    arena = EmapArena{&emap_host, reinterpret_cast<const CUtensorMap*>(ws), kEmapBytes / sizeof(CUtensorMap)};
-    act_top = kEmapBytes;
-    gtop = 0;
+    act_top = gtop = 0;
     planned = false;
     cur = &fwd;
     if (build_network()) return 1;
@@ -1573,8 +1563,6 @@ struct Engine {
       if (emit_batched_grads()) return 1;
     }
     tape.clear();
-    if (!dry && !emap_host.empty())
-      REFID_CUDA_CHECK(cudaMemcpy(ws, emap_host.data(), emap_host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     planned = !dry;
     return 0;
   }

@@ -71,7 +71,7 @@ __device__ __forceinline__ void store32(__nv_bfloat16* ptr, const float* v) {
 // global operands taken from registers (prefetched from global memory or read from the TMA-staged tiles).  On return
 // v = the `out` values and, when e.out2, v2 = out + post.  The rare fp32 / NCHW / pre-activation outputs are written here.
 // GELU (exact erf: ~60 instructions per element, twice) is compiled only into the GELU instantiations.
-template <bool GELU>
+template <bool GELU, bool INPUTS>
 __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2, size_t off, int cseg, int n, int y, int x,
                                            const EpiPF& f, const float* sbias) {
   if (e.bias) {  // bias table of the launch in shared memory (with ~227 KB of smem in use the L1 is too small to cache it)
@@ -82,19 +82,19 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
     }
   }
-  if (e.pre) {
+  if (INPUTS && e.pre) {
     float t[32];
     unpack32(f.a, t);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += t[i];
   }
-  if (e.pre2) {
+  if (INPUTS && e.pre2) {
     float t[32];
     unpack32(f.b, t);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += t[i];
   }
-  if (e.sv) {
+  if (INPUTS && e.sv) {
     float t[32];
     unpack32(f.c, t);
     if (GELU && e.act == ACT_GELU) {
@@ -135,50 +135,12 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       o[i] = t;
     }
   }
-  if (e.out2) {
+  if (INPUTS && e.out2) {
     unpack32(f.c, v2);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v2[i] += v[i];
   }
 }
-
-// ---- TMA-staged epilogue tiles ----------------------------------------------------------------------------------------
-// A pixel-per-lane epilogue touches 32 different 128-byte lines per global access instruction; the L1 pipe then needs more
-// cycles per tile than the tensor core (measured: stores +16 us, one residual +17 us on a 42 us conv).  In staged mode each
-// epilogue warp owns 4 tile rows x 8 pixels x 32 channels sub-tiles (2 KB, 64B-swizzled): inputs arrive by TMA loads
-// issued one group ahead, results leave by TMA stores; the lanes only touch shared memory (conflict-free 16-byte accesses).
-__device__ __forceinline__ uint32_t stage_chunk_addr(uint32_t tile, int lane, int k) {
-  return tile + (uint32_t)lane * 64u + (uint32_t)((k ^ ((lane >> 1) & 3)) << 4);
-}
-__device__ __forceinline__ void stage_read(uint32_t tile, int lane, uint4* q) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[k].x), "=r"(q[k].y), "=r"(q[k].z), "=r"(q[k].w)
-                 : "r"(stage_chunk_addr(tile, lane, k)));
-}
-__device__ __forceinline__ void stage_write(uint32_t tile, int lane, const float* v) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t a = pack_bf16(v[8 * k + 0], v[8 * k + 1]), b = pack_bf16(v[8 * k + 2], v[8 * k + 3]);
-    const uint32_t c = pack_bf16(v[8 * k + 4], v[8 * k + 5]), d = pack_bf16(v[8 * k + 6], v[8 * k + 7]);
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stage_chunk_addr(tile, lane, k)), "r"(a), "r"(b), "r"(c), "r"(d)
-                 : "memory");
-  }
-}
-__device__ __forceinline__ void tma_store_4d_u32(uint32_t src, const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // Shifted taps: a tap (dy,dx) only moves the START ADDRESS of the A descriptor by whole 128-byte pixel rows inside the halo
 // patch.  The 128B swizzle XOR is a function of the absolute shared-memory address bits on both the TMA write and the UMMA
@@ -188,7 +150,7 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 // so the single issuing thread has <= 62 cycles per MMA at N <= 128.  The producer and MMA warps therefore run their
 // loops warp-uniformly (warp index via shuffle, elect.sync only around the issue) so that descriptors live in uniform
 // registers, and every per-MMA descriptor is `base + compile-time constant` (TAPS / pitch / NM are template parameters).
-template <int BN, int NM, int TAPS, int KC, bool GELU>
+template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS>
 __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PITCH = TAPS == 9 ? 10 : 8;       // pixels per patch row in shared memory
@@ -221,11 +183,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
   uint64_t* acc_full = b_empty + kHaloMaxStages;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* wres_bar = acc_empty + 2;
-  uint64_t* ein_bar = wres_bar + 1;  // [4 staged epilogue warps][2 input stages]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ein_bar + 8);
-  // per-warp staging tiles of the TMA epilogue (1024-aligned, after the barriers)
-  uint8_t* estage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023));
-  float* sbias = reinterpret_cast<float*>(estage + (p.epi_tma ? (size_t)4 * (2 * p.n_ein + 2 * p.n_eout) * 2048 : 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
+  // bias table of the launch: [n_blocks * BN] floats, 16-byte aligned (read as float4)
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
   for (int i = threadIdx.x; i < p.n_blocks * BN; i += kHaloThreads) {
     const EpiDesc& e = p.epi[i >> p.epi_shift];
     sbias[i] = e.bias ? __ldg(e.bias + e.coff + (i & (p.epi_seg - 1))) : 0.f;
@@ -243,9 +203,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], p.epi_tma ? 4 : 8);
+      mbar_init(&acc_empty[s], 8);
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&ein_bar[s], 1);
     mbar_init(wres_bar, 1);
     fence_barrier_init();
   }
@@ -387,115 +346,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     constexpr int GPT = BN / 32;  // 32-channel groups per pixel tile
     constexpr int G = NM * GPT;
     const int epi_mask = p.epi_seg - 1;
-    if (p.epi_tma) {
-      // ---- staged mode: warps 2..5; each warp handles all G groups of its 4 tile rows (sub-tiles of 4 x 8 px x 32 ch) ----
-      if (warp < 6) {
-        const int n_in = p.n_ein, n_out = p.n_eout;
-        const uint32_t wst = smem_u32(estage) + (uint32_t)(warp - 2) * (uint32_t)((2 * n_in + 2 * n_out) * 2048);
-        const uint32_t ost0 = wst + (uint32_t)(2 * n_in * 2048);
-        uint32_t st_cnt = 0;
-        uint64_t* ebar = ein_bar + (warp - 2) * 2;
-        uint32_t ld_cnt = 0, rd_cnt = 0;
-        uint32_t it = 0;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-          const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
-          const int x0 = (tile % p.tiles_x) * 8;
-          const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
-          const int n = tile / tiles_per_img;
-          const uint32_t buf = it & 1;
-          // TMA loads of group g's input tiles into input stage (ld_cnt & 1); whole warp calls, one lane issues
-          auto issue_loads = [&](int g) {
-            const int j = g / GPT, ch = nblk * BN + (g % GPT) * 32;
-            const int ei = ch >> p.epi_shift, cseg = ch & epi_mask;
-            const EpiDesc& e = p.epi[ei];
-            const uint32_t st = wst + (ld_cnt & 1u) * (uint32_t)(n_in * 2048);
-            uint64_t* bar = &ebar[ld_cnt & 1u];
-            fence_proxy_async();  // the lanes' earlier generic-proxy reads of this stage precede the async-proxy refill
-            __syncwarp();
-            if (elect_one()) {
-              const int cnt = (e.pre ? 1 : 0) + (e.pre2 ? 1 : 0) + ((e.sv || e.post) ? 1 : 0);
-              if (cnt == 0) {
-                mbar_arrive(bar);
-              } else {
-                mbar_arrive_expect_tx(bar, (uint32_t)cnt * 2048u);
-                const CUtensorMap* mp = p.emaps + ei * 5;
-                const int yr = y0 + j * 16 + q * 4;
-                uint32_t dst = st;
-                if (e.pre) {
-                  tma_load_4d_u32(dst, mp + 2, bar, cseg, x0, yr, n);
-                  dst += 2048;
-                }
-                if (e.pre2) {
-                  tma_load_4d_u32(dst, mp + 3, bar, cseg, x0, yr, n);
-                  dst += 2048;
-                }
-                if (e.sv || e.post) tma_load_4d_u32(dst, mp + 4, bar, cseg, x0, yr, n);
-              }
-            }
-            ++ld_cnt;
-          };
-          if (n_in) issue_loads(0);
-          mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
-          tc_fence_after();
-#pragma unroll 1
-          for (int g = 0; g < G; ++g) {
-            if (n_in && g + 1 < G) issue_loads(g + 1);
-            const int j = g / GPT, c0 = (g % GPT) * 32;
-            const int ch = nblk * BN + c0;
-            const int ei = ch >> p.epi_shift, cseg = ch & epi_mask;
-            const EpiDesc& e = p.epi[ei];
-            const int y = y0 + j * 16 + ty, x = x0 + tx;
-            const bool valid = (y < p.H) && (x < p.W);
-            const size_t pix = ((size_t)n * e.OH + (size_t)y) * e.OW + (size_t)x;
-            const size_t off = pix * (size_t)e.C + e.coff + cseg;
-            float v[32], v2[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c0);
-            tmem_ld16(taddr, v);
-            tmem_ld16(taddr + 16, v + 16);
-            EpiPF f;
-            if (n_in) {
-              const uint32_t st = wst + (rd_cnt & 1u) * (uint32_t)(n_in * 2048);
-              mbar_wait(&ebar[rd_cnt & 1u], (rd_cnt >> 1) & 1, 0x770);
-              uint32_t src = st;
-              if (e.pre) {
-                stage_read(src, lane, f.a);
-                src += 2048;
-              }
-              if (e.pre2) {
-                stage_read(src, lane, f.b);
-                src += 2048;
-              }
-              if (e.sv || e.post) stage_read(src, lane, f.c);
-              ++rd_cnt;
-            }
-            tmem_ld_wait();
-            (void)valid;  // every lane computes: staged inputs of out-of-range pixels are TMA zero fill, stores are clipped
-            epi_math32<GELU>(e, v, v2, off, cseg, n, y, x, f, sbias + ch);
-            // results -> staging tile(s) -> TMA store (out-of-range rows / columns are clipped by the TMA unit)
-            const uint32_t ost = ost0 + (st_cnt & 1u) * (uint32_t)(n_out * 2048);
-            ++st_cnt;
-            if (lane == 0) bulk_wait_read1();  // the stores issued two groups ago have finished reading this buffer
-            __syncwarp();
-            if (e.out) stage_write(ost, lane, v);
-            if (e.out2) stage_write(ost + (e.out ? 2048u : 0u), lane, v2);
-            fence_proxy_async();
-            __syncwarp();
-            if (elect_one()) {
-              const CUtensorMap* mp = p.emaps + ei * 5;
-              const int yr = y0 + j * 16 + q * 4;
-              if (e.out) tma_store_4d_u32(ost, mp + 0, cseg, x0, yr, n);
-              if (e.out2) tma_store_4d_u32(ost + (e.out ? 2048u : 0u), mp + 1, cseg, x0, yr, n);
-              bulk_commit();
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
-      }
-    } else {
+    {
       // ---- direct mode: eight warps, two per TMEM lane quarter splitting the groups (even / odd); global operands
       //      prefetched one group ahead into registers, 256-bit global accesses ----
       const int hsel = (warp - 2) >> 2;
@@ -516,8 +367,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           const size_t pix = ((size_t)n * e->OH + (size_t)(y * e->osy + e->ooy)) * e->OW + (size_t)(x * e->osx + e->oox);
           off = pix * (size_t)e->C + e->coff + cseg;
         };
+        // 32-channel groups of this thread's pixel: TMEM -> registers -> arithmetic -> 256-bit global stores.  INPUTS
+        // instantiations (residuals, masks, skip-sum operands) load group g+2's global operands while group g is
+        // computed; the others carry neither the prefetch registers nor the second output.
         EpiPF cur, nxt;
-        if (hsel < G) {
+        if (INPUTS && hsel < G) {
           const EpiDesc* e;
           size_t off;
           int cseg, y;
@@ -533,23 +387,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           size_t off;
           int cseg, y;
           bool valid;
-          if (g + 2 < G) {
+          if (INPUTS && g + 2 < G) {
             group_ctx(g + 2, e, off, cseg, y, valid);
             epi_prefetch32(*e, off, valid, nxt);
           }
           group_ctx(g, e, off, cseg, y, valid);
           const int j = g / GPT, c0 = (g % GPT) * 32;
-          float v[32], v2[32];
+          float v[32], v2[INPUTS ? 32 : 1];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c0);
           tmem_ld16(taddr, v);
           tmem_ld16(taddr + 16, v + 16);
           tmem_ld_wait();
           if (valid) {
-            epi_math32<GELU>(*e, v, v2, off, cseg, n, y, x, cur, sbias + nblk * BN + c0);
+            epi_math32<GELU, INPUTS>(*e, v, v2, off, cseg, n, y, x, cur, sbias + nblk * BN + c0);
             if (e->out) store32(e->out + off, v);
-            if (e->out2) store32(e->out2 + off, v2);
+            if (INPUTS && e->out2) store32(e->out2 + off, v2);
           }
-          cur = nxt;
+          if (INPUTS) cur = nxt;
         }
         tc_fence_before();
         __syncwarp();
@@ -567,21 +421,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
 }
 
 constexpr size_t kHaloSmemMax = 227 * 1024;
-constexpr size_t kHaloBarBytes = (4 * kHaloMaxStages + 5 + 8) * sizeof(uint64_t) + 32 + 1024;  // + staging alignment
+constexpr size_t kHaloBarBytes = (4 * kHaloMaxStages + 5) * sizeof(uint64_t) + 48;
 
 size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
   const size_t a_bytes = ((size_t)p.patch_rows * p.pitch_px * p.kc * 2 + 1023) & ~(size_t)1023;
   const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
   const size_t b_total = p.resident_b ? (size_t)total_slabs * p.num_taps * BN * p.kc * 2 : (size_t)p.stages_b * BN * p.kc * 2;
-  const size_t staging = (p.epi_tma ? (size_t)4 * (2 * p.n_ein + 2 * p.n_eout) * 2048 : 0) + (size_t)p.n_blocks * BN * 4;
-  return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + staging + 1024;
+  return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + (size_t)p.n_blocks * BN * 4 + 1024;
 }
 
-template <int BN, int NM, int TAPS, int KC, bool GELU>
+template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS>
 int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC, GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
     configured = true;
   }
   static int num_sms = 0;
@@ -591,7 +444,7 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
     REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  haloconv_kernel<BN, NM, TAPS, KC, GELU><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
+  haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS><<<grid, kHaloThreads, halo_smem_bytes(p, BN), stream>>>(p);
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -631,18 +484,25 @@ int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream
   bool gelu = false;
   for (int i = 0; i < kMaxNBlocks; ++i) gelu = gelu || p.epi[i].act == ACT_GELU;
   REFID_REQUIRE(!gelu || (p.num_taps == 1 && p.kc == 64), "haloconv: GELU epilogues are instantiated for 1x1 / 64-channel slabs only");
-#define HINST(bn, nm)                                                                                        \
-  if (BN == bn && NM == nm && p.kc == 64) {                                                                 \
-    if (p.num_taps == 9) return launch_halo_inst<bn, nm, 9, 64, false>(p, stream);                          \
-    return gelu ? launch_halo_inst<bn, nm, 1, 64, true>(p, stream) : launch_halo_inst<bn, nm, 1, 64, false>(p, stream); \
+  const bool in = p.epi_inputs != 0;
+#define HPICK(bn, nm, taps, kc, gl) \
+  return in ? launch_halo_inst<bn, nm, taps, kc, gl, true>(p, stream) : launch_halo_inst<bn, nm, taps, kc, gl, false>(p, stream)
+#define HINST(bn, nm)                                \
+  if (BN == bn && NM == nm && p.kc == 64) {         \
+    if (p.num_taps == 9) HPICK(bn, nm, 9, 64, false); \
+    if (gelu) HPICK(bn, nm, 1, 64, true);            \
+    HPICK(bn, nm, 1, 64, false);                     \
   }
-#define HINST32(bn, nm)                                                                                      \
-  if (BN == bn && NM == nm && p.kc == 32)                                                                   \
-    return p.num_taps == 9 ? launch_halo_inst<bn, nm, 9, 32, false>(p, stream) : launch_halo_inst<bn, nm, 1, 32, false>(p, stream);
+#define HINST32(bn, nm)                              \
+  if (BN == bn && NM == nm && p.kc == 32) {         \
+    if (p.num_taps == 9) HPICK(bn, nm, 9, 32, false); \
+    HPICK(bn, nm, 1, 32, false);                     \
+  }
   HINST(32, 1) HINST(64, 1) HINST(128, 1) HINST(256, 1)
   HINST(32, 2) HINST(64, 2) HINST(128, 2)
   HINST32(32, 1) HINST32(64, 1) HINST32(128, 1)
   HINST32(32, 2) HINST32(64, 2) HINST32(128, 2)
+#undef HPICK
 #undef HINST32
 #undef HINST
   set_error("haloconv: unsupported BN=%d NM=%d", BN, NM);

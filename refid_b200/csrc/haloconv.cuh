@@ -23,9 +23,7 @@ struct HaloConvParams {
   int epi_seg;      // output channels per EpiDesc (power of two, divides BN)
   int epi_shift;    // log2(epi_seg)
   unsigned short tap_mask[kMaxNBlocks];  // per N block: taps to execute (0 = all); streamed-weight path only
-  int epi_tma;      // staged epilogue: inputs by TMA loads, outputs by TMA stores through per-warp shared-memory tiles
-  int n_ein, n_eout;  // staged tiles per group: inputs (pre, pre2, sv|post) and outputs (out, out2), maxima over epi[]
-  const CUtensorMap* emaps;  // device memory: 5 maps per EpiDesc (out, out2, pre, pre2, sv|post), box (32 ch, 8 px, 4 rows, 1)
+  int epi_inputs;   // some EpiDesc reads a global operand (pre, pre2, sv, post)
   int kc;           // channels per K slab: 64 (128B-swizzled pixel rows) or 32 (64B)
   int num_taps;     // 9 or 1
   int halo;         // 1 (3x3) or 0 (1x1)

@@ -215,6 +215,9 @@ CASES = {
     "conv3x3_96_64": lambda: case_conv3x3(cin=96, cout=64, H=24, W=24),
     "dgrad3x3_split_32": lambda: case_dgrad3x3_split(c=32),
     "conv3x3_128_128": lambda: case_conv3x3(cin=128, cout=128, H=8, W=8),
+    "conv3x3_128_128_pair_odd_tiles": lambda: case_conv3x3(cin=128, cout=128, H=32, W=24, N=3, pre=True),
+    "conv3x3_dual_128+128_128_pair": lambda: case_conv3x3(cin=128, cin2=128, cout=128, H=64, W=64, N=2),
+    "conv3x3_256_256_pair": lambda: case_conv3x3(cin=256, cout=256, H=32, W=40, N=2),
     "conv3x3_256_256_h4": lambda: case_conv3x3(cin=256, cout=256, H=4, W=4, N=3),
     "conv3x3_ragged_24x20": lambda: case_conv3x3(H=24, W=20, N=1),
     "conv3x3_64_64_gelu": lambda: case_conv3x3(act=ACT_GELU),
