@@ -16,7 +16,7 @@ constexpr int kHaloMaxStages = 8;
 // on the accumulator, so they are issued one 32-channel group AHEAD of use -- the first group of a tile before the
 // accumulator-ready wait -- instead of load -> ~800-cycle stall -> use in every 16-channel step.
 struct EpiPF {
-  uint4 a[4], b[4], c[4];  // pre, pre2, (sv | post): 32 channels of this thread's pixel each
+  uint4 a[4], c[4];  // pre, (sv | post): 32 channels of this thread's pixel each (pre2 is rare and loaded at use)
 };
 
 __device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, bool valid, EpiPF& f) {
@@ -24,10 +24,6 @@ __device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, boo
   if (e.pre) {
     ldg256(e.pre + off, f.a[0], f.a[1]);
     ldg256(e.pre + off + 16, f.a[2], f.a[3]);
-  }
-  if (e.pre2) {
-    ldg256(e.pre2 + off, f.b[0], f.b[1]);
-    ldg256(e.pre2 + off + 16, f.b[2], f.b[3]);
   }
   const __nv_bfloat16* third = e.sv ? e.sv : e.post;
   if (third) {
@@ -53,6 +49,25 @@ __device__ __forceinline__ void unpack32(const uint4* q, float* f) {
     f[8 * i + 4] = bf16_lo(q[i].z); f[8 * i + 5] = bf16_hi(q[i].z);
     f[8 * i + 6] = bf16_lo(q[i].w); f[8 * i + 7] = bf16_hi(q[i].w);
   }
+}
+// v[8k..8k+7] (+)= the 8 bf16 values of q (one 16-byte chunk): keeps temporaries at 8 registers instead of 32
+__device__ __forceinline__ void add_chunk8(float* v, const uint4& q) {
+  v[0] += bf16_lo(q.x); v[1] += bf16_hi(q.x); v[2] += bf16_lo(q.y); v[3] += bf16_hi(q.y);
+  v[4] += bf16_lo(q.z); v[5] += bf16_hi(q.z); v[6] += bf16_lo(q.w); v[7] += bf16_hi(q.w);
+}
+// out2 = v + post, packed and stored chunk by chunk (no second 32-float array)
+__device__ __forceinline__ void store32_sum(__nv_bfloat16* ptr, const float* v, const uint4* post) {
+  uint4 t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint4 q = post[k];
+    t[k].x = pack_bf16(v[8 * k + 0] + bf16_lo(q.x), v[8 * k + 1] + bf16_hi(q.x));
+    t[k].y = pack_bf16(v[8 * k + 2] + bf16_lo(q.y), v[8 * k + 3] + bf16_hi(q.y));
+    t[k].z = pack_bf16(v[8 * k + 4] + bf16_lo(q.z), v[8 * k + 5] + bf16_hi(q.z));
+    t[k].w = pack_bf16(v[8 * k + 6] + bf16_lo(q.w), v[8 * k + 7] + bf16_hi(q.w));
+  }
+  stg256(ptr, t[0], t[1]);
+  stg256(ptr + 16, t[2], t[3]);
 }
 __device__ __forceinline__ void store32(__nv_bfloat16* ptr, const float* v) {
   uint4 t[4];
@@ -83,27 +98,29 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
     }
   }
   if (INPUTS && e.pre) {
-    float t[32];
-    unpack32(f.a, t);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += t[i];
+    for (int k = 0; k < 4; ++k) add_chunk8(v + 8 * k, f.a[k]);
   }
   if (INPUTS && e.pre2) {
-    float t[32];
-    unpack32(f.b, t);
+    uint4 r[4];
+    ldg256(e.pre2 + off, r[0], r[1]);
+    ldg256(e.pre2 + off + 16, r[2], r[3]);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += t[i];
+    for (int k = 0; k < 4; ++k) add_chunk8(v + 8 * k, r[k]);
   }
   if (INPUTS && e.sv) {
-    float t[32];
-    unpack32(f.c, t);
-    if (GELU && e.act == ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(t[i]);
-    } else {
-      const float sl = e.slope;
+    for (int k = 0; k < 4; ++k) {
+      float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      add_chunk8(t, f.c[k]);
+      if (GELU && e.act == ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= (t[i] > 0.f ? 1.f : sl);
+        for (int i = 0; i < 8; ++i) v[8 * k + i] *= gelu_grad_f(t[i]);
+      } else {
+        const float sl = e.slope;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * k + i] *= (t[i] > 0.f ? 1.f : sl);
+      }
     }
   } else {
     if (e.out_pre) store32(e.out_pre + off, v);
@@ -135,11 +152,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       o[i] = t;
     }
   }
-  if (INPUTS && e.out2) {
-    unpack32(f.c, v2);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v2[i] += v[i];
-  }
+  (void)v2;
 }
 
 // Shifted taps: a tap (dy,dx) only moves the START ADDRESS of the A descriptor by whole 128-byte pixel rows inside the halo
@@ -370,40 +383,49 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         // 32-channel groups of this thread's pixel: TMEM -> registers -> arithmetic -> 256-bit global stores.  INPUTS
         // instantiations (residuals, masks, skip-sum operands) load group g+2's global operands while group g is
         // computed; the others carry neither the prefetch registers nor the second output.
-        EpiPF cur, nxt;
-        if (INPUTS && hsel < G) {
+        auto prefetch = [&](int g, EpiPF& f) {
           const EpiDesc* e;
           size_t off;
           int cseg, y;
           bool valid;
-          group_ctx(hsel, e, off, cseg, y, valid);
-          epi_prefetch32(*e, off, valid, cur);
-        }
-        mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
-        tc_fence_after();
-#pragma unroll 1
-        for (int g = hsel; g < G; g += 2) {
+          group_ctx(g, e, off, cseg, y, valid);
+          epi_prefetch32(*e, off, valid, f);
+        };
+        auto process = [&](int g, const EpiPF& f) {
           const EpiDesc* e;
           size_t off;
           int cseg, y;
           bool valid;
-          if (INPUTS && g + 2 < G) {
-            group_ctx(g + 2, e, off, cseg, y, valid);
-            epi_prefetch32(*e, off, valid, nxt);
-          }
           group_ctx(g, e, off, cseg, y, valid);
           const int j = g / GPT, c0 = (g % GPT) * 32;
-          float v[32], v2[INPUTS ? 32 : 1];
+          float v[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c0);
           tmem_ld16(taddr, v);
           tmem_ld16(taddr + 16, v + 16);
           tmem_ld_wait();
           if (valid) {
-            epi_math32<GELU, INPUTS>(*e, v, v2, off, cseg, n, y, x, cur, sbias + nblk * BN + c0);
+            epi_math32<GELU, INPUTS>(*e, v, nullptr, off, cseg, n, y, x, f, sbias + nblk * BN + c0);
             if (e->out) store32(e->out + off, v);
-            if (INPUTS && e->out2) store32(e->out2 + off, v2);
+            if (INPUTS && e->out2) store32_sum(e->out2 + off, v, f.c);
           }
-          if (INPUTS) cur = nxt;
+        };
+        EpiPF fa, fb;  // two register sets, alternating: no copies
+        if (INPUTS && hsel < G) prefetch(hsel, fa);
+        mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
+        tc_fence_after();
+        if (INPUTS) {
+#pragma unroll 1
+          for (int g = hsel; g < G; g += 4) {
+            if (g + 2 < G) prefetch(g + 2, fb);
+            process(g, fa);
+            if (g + 2 < G) {
+              if (g + 4 < G) prefetch(g + 4, fa);
+              process(g + 2, fb);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int g = hsel; g < G; g += 2) process(g, fa);
         }
         tc_fence_before();
         __syncwarp();
