@@ -167,3 +167,46 @@ def test_optimize_parameters_and_test_callers_match_oracle():
             agree += (torch.sign(d_mine) == torch.sign(d_ref)).double().sum().item()
             total += p.numel()
     assert agree / total > 0.9, agree / total
+
+
+def test_full_resolution_inference_shape():
+    """BASELINE.json configs[4] geometry (1280x720 frame, forward only, eval/no_grad), two event slices to keep the CPU
+    oracle at seconds: 160 x 45 pixel tiles per level-0 conv, ragged tiles at the coarser levels (90 / 45 / 22.5 rows)."""
+    from oracle import refid_oracle as O
+    B, T, H, W, ic, ec = 1, 2, 720, 1280, 6, 2
+    P = paramgen.make_params(O.param_shapes(ic, ec), seed=0)
+    x, ev, _ = paramgen.make_inputs(B, T, H, W, ic, ec, x5d=True)
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    with torch.no_grad():
+        ref = O.forward(P, x, ev)
+    net = _net(ic, ec, P).eval()
+    with torch.no_grad():
+        out = net(x=x.cuda(), event=ev.cuda())
+    _no_abort()
+    assert out.shape == (B, T, 3, H, W)
+    assert (out.cpu() - ref).abs().max().item() < 2e-2
+
+
+def test_highrev_crop_training_step():
+    """BASELINE.json configs[3] geometry (512x512 crops, img_chn 26) at B=1, T=3: loss and gradient norms against the
+    fp32 oracle (norms within 8 %, as for the golden cases)."""
+    from oracle import refid_oracle as O
+    B, T, H, W, ic, ec = 1, 3, 512, 512, 26, 2
+    P = paramgen.make_params(O.param_shapes(ic, ec), seed=0)
+    x, ev, gt = paramgen.make_inputs(B, T, H, W, ic, ec)
+    ref_out, ref_loss, ref_g = O.loss_and_grads(P, x, ev, gt)
+    net = _net(ic, ec, P)
+    out = net(x=x.cuda(), event=ev.cuda())
+    loss = torch.sqrt((out - gt.cuda()) ** 2 + 1e-12).mean()
+    loss.backward()
+    _no_abort()
+    assert (out.detach().cpu() - ref_out).abs().max().item() < 2e-2
+    assert abs(loss.item() - ref_loss.item()) < 2e-3
+    bad = []
+    for n, p in net.named_parameters():
+        if ref_g.get(n) is None or p.grad is None:
+            continue
+        r = ref_g[n].double().norm().item()
+        if r > 0 and abs(p.grad.double().norm().item() - r) > 0.08 * r:
+            bad.append((n, p.grad.double().norm().item(), r))
+    assert not bad, bad[:5]
