@@ -253,16 +253,25 @@ def main():
         if not args.no_profile:
             prof = st["engine"].profile(True)
             torch.cuda.synchronize()
-            conv = {k: prof[k] for k in ("conv_fwd", "conv_dgrad")}
+            # dominant kernel: haloconv_kernel on the stride-1 3x3 convs with >= 64 channels (forward + data-gradient)
+            conv = {k: prof[k] for k in ("conv3x3_fwd", "conv3x3_dgrad")}
             cms = sum(v["ms"] for v in conv.values())
             cfl = sum(v["flops"] for v in conv.values())
             cn = sum(v["launches"] for v in conv.values())
             tot = sum(v["ms"] for v in prof.values())
             ach = cfl / (cms * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "haloconv_kernel / tapgemm_kernel (conv forward + data-gradient implicit GEMM, tcgen05)",
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r01_ncu_haloconv.json")
+            if os.path.exists(tp):  # dram bytes per launch from the committed `ncu --set full` capture of the same kernel
+                caps = [c for c in json.load(open(tp)) if "haloconv" in c.get("kernel", "")]
+                if caps:
+                    traffic = 1e6 * sum(c["dram_read_MB"] + c["dram_write_MB"] for c in caps) / len(caps)
+            line["roofline"] = {"bound": "tensor",
+                                "kernel": "haloconv_kernel (stride-1 3x3 implicit-GEMM conv, >= 64 channels, forward + data-gradient, tcgen05)",
                                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                                 "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                                "traffic": None, "launches_per_step": cn, "avg_launch_ms": cms / max(cn, 1),
+                                "traffic": traffic, "traffic_note": "mean dram read+write bytes per captured launch (profiles/r01_ncu_haloconv.json)",
+                                "launches_per_step": cn, "avg_launch_ms": cms / max(cn, 1),
                                 "share_of_step_device_time": cms / tot,
                                 "per_class": {k: {"ms": v["ms"], "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] else 0.0,
                                                   "launches": v["launches"]} for k, v in prof.items()}}

@@ -75,8 +75,10 @@ int refid_backward(refid_handle h, const float* grad_out, void* stream);
 
 /* Roofline accounting: re-runs forward (+ backward) of the current plan on the tensors of the last call with a CUDA
  * event pair around every launch; sums device milliseconds, algorithmic FLOPs and launch counts per class:
- * [0] conv forward tap-GEMM, [1] data-gradient tap-GEMM, [2] weight-gradient GEMM, [3] memory-bound kernels. */
-int refid_profile(refid_handle h, int with_backward, double ms[4], double flops[4], long launches[4], void* stream);
+ * [0] other conv-shaped forward launches (1x1, 32-channel, stride-2, heads, pred), [1] their data-gradients,
+ * [2] weight-gradient GEMMs, [3] memory-bound kernels, [4] stride-1 3x3 convs with >= 64 channels (halo-conv engine,
+ * the dominant kernel) forward, [5] their data-gradients. */
+int refid_profile(refid_handle h, int with_backward, double ms[6], double flops[6], long launches[6], void* stream);
 
 /* Same replay, one CSV row per launch (pass,index,class,label,ms,gflop) written to `path`. */
 int refid_profile_csv(refid_handle h, int with_backward, const char* path, void* stream);

@@ -94,7 +94,9 @@ struct ConvOp {
 typedef std::function<int(cudaStream_t)> Launch;
 
 // launch classes for the roofline accounting (bench.py)
-enum LaunchClass { LC_CONV_FWD = 0, LC_CONV_DGRAD = 1, LC_WGRAD = 2, LC_OTHER = 3, LC_COUNT = 4 };
+// 4 / 5: the dominant kernel = stride-1 3x3 convs with >= 64 channels on both sides on the halo-conv engine (the EvR
+// trunks, bottleneck, decoder trunks); 0 / 1: every other conv-shaped launch (1x1, 32-channel, stride-2, heads, pred)
+enum LaunchClass { LC_CONV_FWD = 0, LC_CONV_DGRAD = 1, LC_WGRAD = 2, LC_OTHER = 3, LC_MAIN3_FWD = 4, LC_MAIN3_DGRAD = 5, LC_COUNT = 6 };
 struct LaunchMeta {
   int cls;
   double flops;  // algorithmic FLOPs (2*MAC on un-padded channel counts); 0 for memory-bound kernels
@@ -444,6 +446,11 @@ struct Engine {
     (cur == &fwd ? fwd_meta : bwd_meta).push_back(LaunchMeta{cls, flops, cur_label + tag});
   }
 
+  bool main3x3(const ConvOp& op) const {
+    const Site& s = sites[op.site];
+    return op.kind == CK_3X3 && s.R >= 64 && s.Cc >= 64 && s.key != "pred";
+  }
+
   // algorithmic FLOPs of one convolution (forward = data-gradient = weight-gradient)
   double conv_flops(const ConvOp& op) const {
     const Site& s = sites[op.site];
@@ -676,9 +683,9 @@ struct Engine {
         emit([l, self, toff](cudaStream_t st) mutable {
           for (int i = 0; i < l.num_epi(); ++i) l.epi(i)->out_nchw = self->io_out + toff;
           return run_conv(l, st);
-        }, LC_CONV_FWD, conv_flops(op), ":fwd");
+        }, main3x3(op) ? LC_MAIN3_FWD : LC_CONV_FWD, conv_flops(op), ":fwd");
       } else {
-        emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, LC_CONV_FWD, conv_flops(op), ":fwd");
+        emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, main3x3(op) ? LC_MAIN3_FWD : LC_CONV_FWD, conv_flops(op), ":fwd");
       }
     }
     if (train && !op.no_tape) {
@@ -820,7 +827,7 @@ struct Engine {
             }
             TapGemmLaunch l;
             if (build_conv(d, groups, ng, &l)) return 1;
-            emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, LC_CONV_DGRAD,
+            emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, main3x3(op) ? LC_MAIN3_DGRAD : LC_CONV_DGRAD,
                  conv_flops(op) * grad_ch / cin_total / launches, ":dgrad");
           }
         }

@@ -103,9 +103,9 @@ class Engine:
 
     def profile(self, with_backward=True):
         """Per-class device time / algorithmic FLOPs / launch count of one forward(+backward) replay (see header)."""
-        ms, fl, n = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_long * 4)()
+        ms, fl, n = (ctypes.c_double * 6)(), (ctypes.c_double * 6)(), (ctypes.c_long * 6)()
         _lib.check(self.L.refid_profile(self.h, int(with_backward), ms, fl, n, self._stream()), "refid_profile")
-        names = ("conv_fwd", "conv_dgrad", "wgrad", "other")
+        names = ("conv_other_fwd", "conv_other_dgrad", "wgrad", "other", "conv3x3_fwd", "conv3x3_dgrad")
         return {k: {"ms": ms[i], "flops": fl[i], "launches": n[i]} for i, k in enumerate(names)}
 
     def profile_csv(self, path, with_backward=True):

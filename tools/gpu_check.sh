@@ -15,7 +15,7 @@ if [ "$2" = "bench" ]; then
 import json
 try:
     d = json.loads(open("gpurun_out/bench_$tag.log").read().strip().splitlines()[-1])
-    print("BENCH", d["value"], "frames/s", d["ms_per_step"], "ms/step", {k: (round(v["ms"], 1), round(v["tflops"])) for k, v in d["roofline"]["per_class"].items()})
+    print("BENCH", round(d["value"], 1), "frames/s", round(d["ms_per_step"], 2), "ms/step", "roofline frac", round(d["roofline"]["frac"], 3), {k: (round(v["ms"], 1), round(v["tflops"])) for k, v in d["roofline"]["per_class"].items()})
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/bench_$tag.log").read()[-2000:])
 PY

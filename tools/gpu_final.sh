@@ -7,6 +7,6 @@ timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$tag.json 2>
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>&1; tail -c 400 gpurun_out/bench_ref_$tag.json
 timeout 600 python tools/layer_profile.py 8 23 256 256 layersT23_$tag > gpurun_out/layersT23_$tag.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$tag.csv python tools/profile_step.py 2 4 256 256 > gpurun_out/ncu_list_$tag.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"haloconv_kernel<\(int\)(64|128|256), \(int\)[12], \(int\)9, \(int\)64" -s 10 -c 14 -f -o gpurun_out/prof_haloconv_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_halo_$tag.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:halowgrad -c 8 -f -o gpurun_out/prof_halowgrad_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_wgrad_$tag.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"haloconv_kernel<\(int\)(64|128|256), \(int\)[12], \(int\)9, \(int\)64" -s 10 -c 7 -f -o gpurun_out/prof_haloconv_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_halo_$tag.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:halowgrad -c 3 -f -o gpurun_out/prof_halowgrad_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_wgrad_$tag.log 2>&1
 ls -la gpurun_out/*.ncu-rep
