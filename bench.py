@@ -142,7 +142,7 @@ def cpu_reference_run(B, T, H, W, ic, ec, steps, warmup, sample_T=None, sample_h
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gopro_11p1", choices=list(WORKLOADS))

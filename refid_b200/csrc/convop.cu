@@ -63,7 +63,8 @@ int fill_taps(int kind, int parity, TapTable* t) {
       return 0;
     }
     case CK_DOWN4_DGRAD_HALO:
-      set_error("CK_DOWN4_DGRAD_HALO needs 64-channel-multiple operands (halo-conv engine only)");
+    case CK_DOWN4_HALO:
+      set_error("halo-only conv kind %d needs 64-channel-multiple operands and even H, W", kind);
       return 1;
     case CK_UP2_DGRAD:
       t->n = 4;
@@ -86,8 +87,11 @@ static int make_patch_map(CUtensorMap* m, const ActSrc& s, int N, int H, int W, 
 // Returns 1 when the op was lowered onto the halo-conv engine, 0 when it does not qualify, -1 on error.
 static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out) {
   const bool down_dgrad = d.kind == CK_DOWN4_DGRAD_HALO;
-  if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad) return 0;
+  const bool down_fwd = d.kind == CK_DOWN4_HALO;  // 3x3 over the four stride-2 parity views of the single source
+  if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad && !down_fwd) return 0;
   if (down_dgrad && ngroups != 1) return 0;
+  if (down_fwd && (d.nsrc != 1 || d.src[0].C % 64 || (d.H & 1) || (d.W & 1) || 4 * (d.src[0].C / 64) > 16)) return 0;
+  const int GH = down_fwd ? d.H / 2 : d.H, GW = down_fwd ? d.W / 2 : d.W;  // grid the pixel tiles run over
   for (int g = 0; g < ngroups; ++g)  // GELU epilogues exist on the halo engine for 1x1 convs only (EGACA); else tap-GEMM
     if (groups[g].epi.act == ACT_GELU && d.kind != CK_1X1) return 0;
   static const int disabled = getenv("REFID_NO_HALO") ? 1 : 0;
@@ -98,6 +102,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     if (d.src[s].C % 64) kc = 32;  // 32-channel slabs: 64-byte pixel rows, 64B swizzle
     ktot += d.src[s].C;
   }
+  if (down_fwd) ktot *= 4;
   if (ktot != d.w_cols) return 0;
   int total = 0, seg = 1 << 30;
   for (int g = 0; g < ngroups; ++g) {
@@ -119,9 +124,28 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.pitch_px = h.halo ? 10 : 8;
   h.wrows_per_tap = d.wrows_per_tap;
   h.w_row0 = d.w_row0;
-  h.nsrc = d.nsrc;
+  h.nsrc = down_fwd ? 4 : d.nsrc;
   h.kc = kc;
-  for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / kc;
+  for (int s = 0; s < h.nsrc; ++s) h.src_slabs[s] = d.src[down_fwd ? 0 : s].C / kc;
+  if (down_fwd) {
+    // parity view q = (py,px) holds in[2i+py][2j+px]; input row 2Y+ky-1 = 2(Y+dy)+py  =>  py = 0 uses dy in {0,+1},
+    // py = 1 uses dy in {-1,0} (same in x): 4 of the 9 taps per view, 16 (view, tap) pairs = the 16 kernel taps
+    const int per_q = d.src[0].C / kc;
+    h.masked = 1;
+    int tiles = 0;
+    for (int ks = 0; ks < 4 * per_q; ++ks) {
+      const int py = (ks / per_q) >> 1, px = (ks / per_q) & 1;
+      unsigned m = 0;
+      for (int t9 = 0; t9 < 9; ++t9) {
+        const int dy = t9 / 3 - 1, dx = t9 % 3 - 1;
+        if ((py ? dy <= 0 : dy >= 0) && (px ? dx <= 0 : dx >= 0)) m |= 1u << t9;
+      }
+      h.slab_mask[ks] = (unsigned short)m;
+      h.slab_b0[ks] = (unsigned char)tiles;
+      tiles += 4;
+    }
+    h.resident_tiles = tiles;
+  }
   h.n_blocks = (down_dgrad ? 4 : 1) * (total / BN);
   if (h.n_blocks > kMaxNBlocks || (down_dgrad && 4 * (total / seg) > kMaxNBlocks)) return 0;
   if (down_dgrad) {
@@ -142,8 +166,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.epi_shift = 0;
   while ((1 << h.epi_shift) < seg) ++h.epi_shift;
   h.N = d.N;
-  h.H = d.H;
-  h.W = d.W;
+  h.H = GH;
+  h.W = GW;
   int n_ein = 0;
   for (int g = 0; g < ngroups; ++g) {
     const EpiDesc& e = groups[g].epi;
@@ -152,18 +176,25 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.epi_inputs = n_ein > 0;
   // preference: resident weights (two pixel tiles per item, else one) before streamed weights -- re-streaming the
   // weights of a C=64 dual-source conv per 256-pixel item costs more than the smaller M (measured 111 vs 83 us MMA-side)
-  const int nm_pref = (2 * 2 * BN <= 512 && d.H > 16) ? 2 : 1;
+  const int nm_pref = (2 * 2 * BN <= 512 && GH > 16) ? 2 : 1;
   int NM = 0;
   if (haloconv_plan(&h, BN, nm_pref, 1)) NM = nm_pref;
   else if (haloconv_plan(&h, BN, 1, 1)) NM = 1;
   else if (haloconv_plan(&h, BN, nm_pref, 2)) NM = nm_pref;
   else if (haloconv_plan(&h, BN, 1, 2)) NM = 1;
   if (!NM) return 0;
-  h.tiles_x = (d.W + 7) / 8;
-  h.tiles_y = (d.H + 16 * NM - 1) / (16 * NM);
+  h.tiles_x = (GW + 7) / 8;
+  h.tiles_y = (GH + 16 * NM - 1) / (16 * NM);
   h.num_items = h.tiles_x * h.tiles_y * d.N * h.n_blocks;
-  for (int s = 0; s < d.nsrc; ++s)
-    if (make_patch_map(&h.tmA[s], d.src[s], d.N, d.H, d.W, h.pitch_px, h.patch_rows, kc)) return -1;
+  if (down_fwd) {
+    for (int q = 0; q < 4; ++q)
+      if (make_act_map(&h.tmA[q], d.src[0].ptr, d.N, d.H, d.W, d.src[0].pitch, d.src[0].C, q >> 1, q & 1, 2, kc, h.pitch_px,
+                       h.patch_rows, 1))
+        return -1;
+  } else {
+    for (int s = 0; s < d.nsrc; ++s)
+      if (make_patch_map(&h.tmA[s], d.src[s], d.N, d.H, d.W, h.pitch_px, h.patch_rows, kc)) return -1;
+  }
   if (make_mat_map(&h.tmB, d.w, d.w_rows, d.w_cols, kc, BN)) return -1;
   int nd = 0;
   for (int q = 0; q < (down_dgrad ? 4 : 1); ++q)
@@ -174,8 +205,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
         e.osy = e.osx = down_dgrad ? 2 : 1;
         e.ooy = down_dgrad ? (q >> 1) : 0;
         e.oox = down_dgrad ? (q & 1) : 0;
-        e.OH = down_dgrad ? 2 * d.H : d.H;
-        e.OW = down_dgrad ? 2 * d.W : d.W;
+        e.OH = down_dgrad ? 2 * d.H : GH;
+        e.OW = down_dgrad ? 2 * d.W : GW;
         h.epi[nd++] = e;
       }
   out->use_halo = 1;

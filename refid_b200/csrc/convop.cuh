@@ -15,6 +15,8 @@ enum ConvKind : int {
   CK_DOWN4_DGRAD = 4,  // data-gradient of CK_DOWN4 for ONE output parity (4 taps on dY, stride-2 scatter); 4 launches
   CK_UP2_DGRAD = 5,    // data-gradient of CK_UP2: 2x2 stride-2 conv over dOut (4 taps, parity views); grid H/2 x W/2
   CK_ROWS5 = 6,        // 5x5 head conv on an x-unrolled input (channel = kx*Cin + c): 5 vertical taps dy=-2..2
+  CK_DOWN4_HALO = 8,       // CK_DOWN4 forward on the halo-conv engine: a 3x3 conv over the four stride-2 parity views of the
+                           // input (K = 4*Cin), each view using 4 of the 9 taps (weights [tap9][Cout][parity*Cin])
   CK_DOWN4_DGRAD_HALO = 7  // data-gradient of CK_DOWN4, all four output parities in ONE halo-conv launch: the four parities
                            // read the same 3x3 neighbourhood of dY, each uses 4 of its 9 taps (weights [tap9][parity][Cin][Cout])
 };

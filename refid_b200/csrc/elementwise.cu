@@ -552,7 +552,8 @@ __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ f
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int t = (int)(i / per_tap);
     const long r = i % per_tap;
-    const long dst = d.dst_off + (d.dst_tap_stride ? (long)t * d.dst_tap_stride + r : i);
+    long dst = d.dst_off + (d.dst_tap_stride ? (long)t * d.dst_tap_stride + r : i);
+    if (d.transpose && d.dst_pitch) dst = d.dst_off + (long)t * (d.dst_tap_stride ? d.dst_tap_stride : per_tap) + (r / d.R) * d.dst_pitch + r % d.R;
     if (d.tapmap[t] < 0) {
       wpack[dst] = __float2bfloat16(0.f);
       continue;

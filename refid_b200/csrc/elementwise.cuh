@@ -79,6 +79,7 @@ struct PackDesc {
   long dst_off;  // bf16 elements
   int ntaps, R, Cc, transpose;
   long dst_tap_stride;  // elements between destination taps (0: contiguous, R*Cc)
+  int dst_pitch;        // transpose mode: elements between destination rows (0: R)
   signed char tapmap[16];  // source tap of destination tap i; -1: zero block
 };
 int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_dev, int ndesc, long max_elems, cudaStream_t st);

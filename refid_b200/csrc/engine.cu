@@ -204,7 +204,31 @@ struct Engine {
         if (dgrad_pack) s.dgrad_off = add_pack(0, flip);
         break;
       case SK_DOWN4:
-        if (fwd_pack) s.fwd_off = add_pack(1, ident);
+        if (fwd_pack) {
+          // forward on the halo-conv engine: [tap9][Cout][parity q * Cin + ci] (K = 4*Cin), zero where view q does not
+          // use the tap; view q = (py,px), tap (dy,dx): ky = 2*dy + py + 1, kx = 2*dx + px + 1
+          s.fwd_off = pack_elems;
+          for (int q = 0; q < 4; ++q) {
+            PackDesc d;
+            memset(&d, 0, sizeof(d));
+            d.src_off = s.w_off;
+            d.dst_off = pack_elems + (long)q * R;
+            d.ntaps = 9;
+            d.R = R;
+            d.Cc = Cc;
+            d.transpose = 1;
+            d.dst_tap_stride = 4L * R * Cc;
+            d.dst_pitch = 4 * R;
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const int ky = 2 * (t9 / 3 - 1) + (q >> 1) + 1, kx = 2 * (t9 % 3 - 1) + (q & 1) + 1;
+              d.tapmap[t9] = (signed char)((ky >= 0 && ky < 4 && kx >= 0 && kx < 4) ? ky * 4 + kx : -1);
+            }
+            packs.push_back(d);
+          }
+          pack_elems = (pack_elems + 36L * R * Cc + 63) / 64 * 64;
+          if (9L * R * Cc > pack_max) pack_max = 9L * R * Cc;
+          (void)ident;
+        }
         if (dgrad_pack) {
           // data-gradient on the halo-conv engine: [tap9 of the dY neighbourhood][output parity q][Cin][Cout], zero blocks
           // where the parity does not use the tap (ky = qy + 1 - 2*dy, kx = qx + 1 - 2*dx outside the 4x4 kernel)
@@ -647,6 +671,11 @@ struct Engine {
       d.w_cols = cin_total;
       d.wrows_per_tap = cout;
       d.w_row0 = 0;
+      if (op.kind == CK_DOWN4) {  // forward of the stride-2 conv runs as a masked 3x3 over the four parity views
+        d.kind = CK_DOWN4_HALO;
+        d.w_rows = 9L * cout;
+        d.w_cols = 4 * cin_total;
+      }
       const int expect_cin = (op.kind == CK_UP2) ? s.Cc : s.R;
       if (cin_total != expect_cin) {
         set_error("conv %s: input channels %d != %d", s.key.c_str(), cin_total, expect_cin);

@@ -184,10 +184,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int SA = p.stages_a, SB = p.stages_b;
-  const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
+  int total_slabs = 0;
+  for (int i = 0; i < p.nsrc; ++i) total_slabs += p.src_slabs[i];
   uint8_t* a_base = smem;
   uint8_t* b_base = smem + (size_t)SA * A_BYTES;
-  const size_t b_total = p.resident_b ? (size_t)total_slabs * TAPS * B_TILE : (size_t)SB * B_TILE;
+  const size_t b_total = p.resident_b ? (size_t)(p.masked ? p.resident_tiles : total_slabs * TAPS) * B_TILE : (size_t)SB * B_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + b_total);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kHaloMaxStages;
@@ -238,9 +239,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
       tma_prefetch_desc(&p.tmB);
       if (p.resident_b) {
         mbar_arrive_expect_tx(wres_bar, (uint32_t)b_total);
+        int idx = 0;
         for (int ks = 0; ks < total_slabs; ++ks)
-          for (int tap = 0; tap < TAPS; ++tap)
-            tma_load_2d(b_base + (size_t)(ks * TAPS + tap) * B_TILE, &p.tmB, wres_bar, ks * KC, p.w_row0 + tap * p.wrows_per_tap);
+          for (int tap = 0; tap < TAPS; ++tap) {
+            if (p.masked && !((p.slab_mask[ks] >> tap) & 1u)) continue;  // masked: only the used (slab, tap) tiles, compact
+            tma_load_2d(b_base + (size_t)(p.masked ? idx : ks * TAPS + tap) * B_TILE, &p.tmB, wres_bar, ks * KC,
+                        p.w_row0 + tap * p.wrows_per_tap);
+            ++idx;
+          }
       }
     }
     uint32_t ia = 0, ib = 0;
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           }
           ++ia;
           if (!p.resident_b) {
-            const unsigned tmask = p.tap_mask[nblk] ? p.tap_mask[nblk] : 0xFFFFu;
+            const unsigned tmask = (p.tap_mask[nblk] ? p.tap_mask[nblk] : 0xFFFFu) & (p.slab_mask[ks] ? p.slab_mask[ks] : 0xFFFFu);
             for (int tap = 0; tap < TAPS; ++tap) {
               if (!((tmask >> tap) & 1u)) continue;
               const int sb = ib % SB;
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     uint32_t ia = 0, ib = 0, it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
-      const unsigned tmask = p.tap_mask[item % p.n_blocks] ? p.tap_mask[item % p.n_blocks] : 0xFFFFu;
+      const unsigned nmask = p.tap_mask[item % p.n_blocks] ? p.tap_mask[item % p.n_blocks] : 0xFFFFu;
       bool first = true;  // the first MMA of the item overwrites the accumulator
       mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x730 + buf);
       tc_fence_after();
@@ -296,7 +302,34 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         mbar_wait(&a_full[sa], (ia / SA) & 1, 0x740 + sa);
         tc_fence_after();
         const uint64_t a_desc0 = make_smem_desc(a_base_u + (uint32_t)sa * A_BYTES, 16, SBO, SWZ);
-        if (p.resident_b) {
+        const unsigned tmask = nmask & (p.slab_mask[ks] ? p.slab_mask[ks] : 0xFFFFu);
+        if (p.resident_b && p.masked) {
+          // resident, compact weight tiles: only the taps this K slab uses (runtime tap loop, no weight barriers)
+          int bt = p.slab_b0[ks];
+#pragma unroll 1
+          for (int tap = 0; tap < TAPS; ++tap) {
+            if (!((tmask >> tap) & 1u)) continue;
+            const uint32_t tap_off = (uint32_t)((TAPS == 9 ? tap / 3 : 0) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * PXB;
+            const uint64_t a_desc = a_desc0 + (uint64_t)(tap_off >> 4);
+            const uint64_t b_desc = make_smem_desc(b_base_u + (uint32_t)bt * B_TILE, 16, SBO_B, SWZ);
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < NM; ++j) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint64_t ad = a_desc + (uint64_t)(((uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
+                  const uint64_t bd = b_desc + (uint64_t)(((uint32_t)k * 32u) >> 4);
+                  umma_bf16(acc + j * BN, ad, bd, IDESC, (!first || k > 0) ? 1u : 0u);
+                }
+              }
+            }
+            __syncwarp();
+            first = false;
+            ++bt;
+          }
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
+        } else if (p.resident_b) {
           const uint64_t b_desc0 = make_smem_desc(b_base_u + (uint32_t)(ks * TAPS) * B_TILE, 16, SBO_B, SWZ);
           if (elect_one()) {
 #pragma unroll
@@ -447,8 +480,10 @@ constexpr size_t kHaloBarBytes = (4 * kHaloMaxStages + 5) * sizeof(uint64_t) + 4
 
 size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
   const size_t a_bytes = ((size_t)p.patch_rows * p.pitch_px * p.kc * 2 + 1023) & ~(size_t)1023;
-  const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
-  const size_t b_total = p.resident_b ? (size_t)total_slabs * p.num_taps * BN * p.kc * 2 : (size_t)p.stages_b * BN * p.kc * 2;
+  int total_slabs = 0;
+  for (int i = 0; i < p.nsrc; ++i) total_slabs += p.src_slabs[i];
+  const size_t b_total = p.resident_b ? (size_t)(p.masked ? p.resident_tiles : total_slabs * p.num_taps) * BN * p.kc * 2
+                                      : (size_t)p.stages_b * BN * p.kc * 2;
   return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + (size_t)p.n_blocks * BN * 4 + 1024;
 }
 
@@ -476,7 +511,8 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
 int haloconv_plan(HaloConvParams* p, int BN, int NM, int mode) {
   if (2 * NM * BN > 512) return 0;
   p->patch_rows = 16 * NM + 2 * p->halo;
-  const int total_slabs = p->src_slabs[0] + (p->nsrc > 1 ? p->src_slabs[1] : 0);
+  int total_slabs = 0;
+  for (int i = 0; i < p->nsrc; ++i) total_slabs += p->src_slabs[i];
   // weights resident for the whole kernel when they fit next to >= 2 activation stages
   if (p->n_blocks == 1 && mode != 2) {
     p->resident_b = 1;

@@ -17,7 +17,8 @@
 namespace refid {
 
 struct HaloConvParams {
-  CUtensorMap tmA[2];  // per source: dims (C, W, H, N), box (64, pitch_px, patch_rows, 1), 128B swizzle
+  CUtensorMap tmA[4];  // per source: dims (C, W, H, N), box (64, pitch_px, patch_rows, 1), 128B swizzle (the stride-2 `down`
+                       // forward conv has four sources: the stride-2 parity views of its input)
   CUtensorMap tmB;     // packed weights [rows][K], box (64, BN)
   EpiDesc epi[kMaxNBlocks];
   int epi_seg;      // output channels per EpiDesc (power of two, divides BN)
@@ -30,7 +31,10 @@ struct HaloConvParams {
   int pitch_px;     // pixels per patch row in shared memory (multiple of 8)
   int patch_rows;   // 16*NM + 2*halo
   int wrows_per_tap, w_row0;
-  int nsrc, src_slabs[2];
+  int nsrc, src_slabs[4];
+  unsigned short slab_mask[16];  // per K slab: taps to execute (0 = all); with `masked`, resident weight tiles are compact
+  unsigned char slab_b0[16];     // masked + resident: index of the slab's first weight tile
+  int masked, resident_tiles;
   int n_blocks;
   int tiles_x, tiles_y, N, H, W;  // tiles are 8 wide x 16*NM high
   int num_items;                  // tiles * n_blocks

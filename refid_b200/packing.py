@@ -70,3 +70,18 @@ def pack_down_dgrad_halo(w):
             if 0 <= ky < 4 and 0 <= kx < 4:
                 out[t9, q] = w[:, :, ky, kx].t()
     return out.reshape(36 * ci, co).contiguous()
+
+
+def pack_down_fwd_halo(w):
+    """Forward of the 4x4 stride-2 pad-1 conv on the halo-conv engine (csrc/convop.cuh CK_DOWN4_HALO): a 3x3 conv over the
+    four stride-2 parity views q = (py,px) of the input, K = 4*Cin: rows = tap9*Cout + co, cols = q*Cin + ci,
+    value = W[co,ci,ky,kx] with ky = 2*dy + py + 1, kx = 2*dx + px + 1 when inside the kernel, else 0."""
+    co, ci, _, _ = w.shape
+    out = torch.zeros(9, co, 4, ci, dtype=w.dtype, device=w.device)
+    for t9 in range(9):
+        dy, dx = t9 // 3 - 1, t9 % 3 - 1
+        for q in range(4):
+            ky, kx = 2 * dy + (q >> 1) + 1, 2 * dx + (q & 1) + 1
+            if 0 <= ky < 4 and 0 <= kx < 4:
+                out[t9, :, q, :] = w[:, :, ky, kx]
+    return out.reshape(9 * co, 4 * ci).contiguous()

@@ -8,6 +8,7 @@ from refid_b200 import _lib, packing
 
 CK_3X3, CK_1X1, CK_DOWN4, CK_UP2, CK_DOWN4_DGRAD, CK_UP2_DGRAD = range(6)
 CK_DOWN4_DGRAD_HALO = 7
+CK_DOWN4_HALO = 8
 ACT_NONE, ACT_LRELU, ACT_GELU = 0, 1, 2
 
 
@@ -126,6 +127,21 @@ def case_down4(N=2, H=16, W=16, c=64):
     return _err(nchw(o["out"]), ref)
 
 
+def case_down4_halo(N=2, H=32, W=32, c=64, post=False):
+    """Stride-2 conv as a masked 3x3 over the four parity views (halo-conv engine), optional skip-sum second output."""
+    x = rb(g(N, c, H, W, seed=1))
+    w = rb(g(c, c, 4, 4, seed=2) / (4 * c ** 0.5))
+    ref = F.conv2d(x, w, None, stride=2, padding=1)
+    po = rb(g(N, c, H // 2, W // 2, seed=6)) if post else None
+    o = run_conv(CK_DOWN4_HALO, [nhwc(x)], packing.pack_down_fwd_halo(w).to(torch.bfloat16), c, c, (N, H // 2, W // 2),
+                 post=nhwc(po) if post else None)
+    e1 = _err(nchw(o["out"]), ref)
+    if post:
+        e2 = _err(nchw(o["out2"]), ref + po)
+        return max(e1[0], e2[0]), max(e1[1], e2[1])
+    return e1
+
+
 def case_up2(N=2, H=8, W=8, cin=128, cout=64):
     x = rb(g(N, cin, H, W, seed=1))
     w = rb(g(cin, cout, 2, 2, seed=2) / cin ** 0.5)
@@ -227,6 +243,10 @@ CASES = {
     "down4_128_ragged": lambda: case_down4(c=128, H=12, W=20, N=1),
     "up2_128_64": lambda: case_up2(),
     "up2_64_32": lambda: case_up2(cin=64, cout=32),
+    "down4_halo_64": lambda: case_down4_halo(),
+    "down4_halo_64_ragged_post": lambda: case_down4_halo(H=40, W=24, N=3, post=True),
+    "down4_halo_128": lambda: case_down4_halo(c=128, H=48, W=32, N=2),
+    "down4_halo_256": lambda: case_down4_halo(c=256, H=16, W=16, N=2, post=True),
     "down4_dgrad_64": lambda: case_down4_dgrad(),
     "down4_dgrad_halo_64": lambda: case_down4_dgrad_halo(),
     "down4_dgrad_halo_128_ragged": lambda: case_down4_dgrad_halo(c=128, H=20, W=12, N=3),
