@@ -323,6 +323,7 @@ static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLa
   int mode = 0;
   if (q.C == 64) mode = 64;
   else if (q.C % 128 == 0) mode = 128;
+  else if (q.C == 32) mode = 32;
   if (!mode) return 0;
   int cp_total = 0;
   for (int s = 0; s < d.nsrc; ++s) {
@@ -337,15 +338,16 @@ static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLa
   h.CQ = q.C;
   h.cp_total = cp_total;
   h.nsrc = d.nsrc;
-  for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / 64;
-  h.total_slabs = cp_total / 64;
+  const int slab_c = mode == 32 ? 32 : 64;
+  for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / slab_c;
+  h.total_slabs = cp_total / slab_c;
   h.N = d.N;
   h.H = d.H;
   h.W = d.W;
   h.tiles_x = (d.W + 7) / 8;
   h.tiles_y = (d.H + 15) / 16;
   h.num_tiles = h.tiles_x * h.tiles_y * d.N;
-  h.jobs = mode == 64 ? h.total_slabs : (h.total_slabs / 2) * 3 * (q.C / 128);
+  h.jobs = mode == 128 ? (h.total_slabs / 2) * 3 * (q.C / 128) : h.total_slabs;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -355,10 +357,10 @@ static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLa
   h.chunks = num_sms / h.jobs;
   if (h.chunks < 1) h.chunks = 1;
   if (h.chunks > h.num_tiles) h.chunks = h.num_tiles;
-  const int rows = mode == 64 ? 18 : 16;
+  const int rows = mode == 128 ? 16 : 18;
   for (int s = 0; s < d.nsrc; ++s)
-    if (make_act_map(&h.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, 64, 10, rows, 1)) return -1;
-  if (make_act_map(&h.tmQ, q.ptr, d.N, d.H, d.W, q.pitch, q.C, 0, 0, 1, 64, 8, 16, 1)) return -1;
+    if (make_act_map(&h.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, slab_c, 10, rows, 1)) return -1;
+  if (make_act_map(&h.tmQ, q.ptr, d.N, d.H, d.W, q.pitch, q.C, 0, 0, 1, slab_c, 8, 16, 1)) return -1;
   l->use_halo = 1;
   l->bias_done = d.bias_grad != nullptr;
   return 1;

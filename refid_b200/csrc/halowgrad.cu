@@ -12,6 +12,9 @@
 //            difference of the two taps inside the patch.  5 MMA groups (4 pairs + the last tap), N = 64, 320 TMEM columns.
 //   MODE 128 (Cout % 128 == 0): job = (pair of X slabs, one kernel row dy, 128-channel block of Cout).  M = 128 = the two
 //            slabs (LBO = slab stride in shared memory), one MMA group per dx, N = 128, 384 TMEM columns.
+//   MODE 32  (Cout = 32, 32-channel slabs, 64-byte pixel rows / 64B swizzle): job = one 32-channel slab, all 9 taps.  M = 128 =
+//            FOUR 32-row blocks one pixel (64 B) apart = the three dx taps of one kernel row + a don't-care block; one MMA
+//            group per dy, N = 32, 96 TMEM columns.
 //
 // Accumulation stays in TMEM over the CTA's whole pixel range (all T*B images of the batched launch); the fp32 result is
 // added to global memory once per CTA with vectorised reductions.
@@ -52,6 +55,17 @@ struct HWCfg<128> {
   static constexpr int GROUPS = 3, N = 128, COLS = 512;     // 384 used
 };
 
+template <>
+struct HWCfg<32> {
+  static constexpr int ROWS = 18;
+  static constexpr uint32_t P_BYTES = 18 * PITCH * 64;      // one 32-channel slab patch (11520 B)
+  static constexpr uint32_t P_ALLOC = 12288;                // 1024-aligned (the don't-care block may read past the patch)
+  static constexpr uint32_t Q_BYTES = 128 * 32 * 2;         // 8 KB
+  static constexpr uint32_t STAGE = P_ALLOC + Q_BYTES;      // 20480
+  static constexpr uint32_t TX = P_BYTES + Q_BYTES;
+  static constexpr int GROUPS = 3, N = 32, COLS = 128;      // 96 used
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_constant__ HaloWgradParams p) {
   using Cfg = HWCfg<MODE>;
@@ -72,7 +86,7 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
   const int t_begin = (int)(((long)p.num_tiles * chunk) / p.chunks);
   const int t_end = (int)(((long)p.num_tiles * (chunk + 1)) / p.chunks);
   int slab, dy = 0, coblk = 0;  // slab: global 64-channel slab index (MODE 64) or first slab of the pair (MODE 128)
-  if (MODE == 64) {
+  if (MODE == 64 || MODE == 32) {
     slab = job;
   } else {
     const int pairs = p.total_slabs / 2;
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
   const int slab_in_src = slab - (src ? p.src_slabs[0] : 0);
 
   // bias gradient: one job per Cout block also column-sums the G tiles it streams (4 extra arrivals free a stage)
-  const bool colsum = p.bias_out != nullptr && (MODE == 64 ? job == 0 : (slab == 0 && dy == -1));
+  const bool colsum = p.bias_out != nullptr && (MODE == 128 ? (slab == 0 && dy == -1) : job == 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHWMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -120,8 +134,8 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
         if (elect_one()) {
           uint8_t* st = smem + (size_t)s * Cfg::STAGE;
           mbar_arrive_expect_tx(&full_bar[s], Cfg::TX);
-          if (MODE == 64) {
-            tma_load_4d(st, &p.tmP[src], &full_bar[s], slab_in_src * 64, x0 - 1, y0 - 1, n);
+          if (MODE == 64 || MODE == 32) {
+            tma_load_4d(st, &p.tmP[src], &full_bar[s], slab_in_src * MODE, x0 - 1, y0 - 1, n);
             tma_load_4d(st + Cfg::P_ALLOC, &p.tmQ, &full_bar[s], 0, x0, y0, n);
           } else {
             tma_load_4d(st, &p.tmP[src], &full_bar[s], slab_in_src * 64, x0 - 1, y0 + dy, n);
@@ -136,7 +150,8 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem_u = smem_u32(smem);
       constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::N, 1, 1);
-      constexpr uint32_t SBO_A = PITCH * 128;  // next 8-pixel K group = next tile row of the patch
+      constexpr uint32_t PXB = MODE == 32 ? 64u : 128u;  // bytes per pixel row of a slab
+      constexpr uint32_t SBO_A = PITCH * PXB;          // next 8-pixel K group = next tile row of the patch
       int it = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const int s = it % S;
@@ -144,9 +159,19 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
         tc_fence_after();
         const uint32_t st = smem_u + (uint32_t)s * Cfg::STAGE;
         // B: G tile [128 px][64 co] per half; K step = 16 pixel rows of 128 B = 2048 B; halves 16 KB apart
-        const uint64_t bd0 = make_smem_desc(st + Cfg::P_ALLOC, 16384, 1024, 2u);
+        const uint64_t bd0 = make_smem_desc(st + Cfg::P_ALLOC, 16384, 8u * PXB, MODE == 32 ? 4u : 2u);
         if (elect_one()) {
-          if (MODE == 64) {
+          if (MODE == 32) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g) {  // g = kernel row; the four M blocks are the pixels dx = -1, 0, +1, (+2: discarded)
+                const uint32_t offa = (uint32_t)((2 * ks + g) * (int)PITCH) * 64u;
+                const uint64_t ad = make_smem_desc(st + offa, 64u, SBO_A, 4u);
+                umma_bf16(tm + (uint32_t)(g * 32), ad, bd0 + (uint64_t)(ks * 64), IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+          } else if (MODE == 64) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
@@ -179,7 +204,45 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
       // ---------------- epilogue: TMEM -> fp32 global reductions, once per CTA ----------------
       const int q = warp & 3;
       const int m = q * 32 + lane;  // accumulator row
-      if (colsum) {
+      if (colsum && MODE == 32) {
+        // thread m sums pixel row m of the [128 px][32 co] G tile (64-byte rows, 64B swizzle)
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        const uint32_t smem_u = smem_u32(smem);
+        int it = 0;
+        for (int t = t_begin; t < t_end; ++t, ++it) {
+          const int s = it % S;
+          mbar_wait(&full_bar[s], (it / S) & 1, 0x830 + s);
+          const uint32_t gt = smem_u + (uint32_t)s * Cfg::STAGE + Cfg::P_ALLOC;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                         : "r"(gt + (uint32_t)m * 64u + (uint32_t)((k ^ ((m >> 1) & 3)) << 4)));
+            acc[8 * k + 0] += bf16_lo(u.x); acc[8 * k + 1] += bf16_hi(u.x);
+            acc[8 * k + 2] += bf16_lo(u.y); acc[8 * k + 3] += bf16_hi(u.y);
+            acc[8 * k + 4] += bf16_lo(u.z); acc[8 * k + 5] += bf16_hi(u.z);
+            acc[8 * k + 6] += bf16_lo(u.w); acc[8 * k + 7] += bf16_hi(u.w);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = acc[i];
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          acc[i] = v;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(p.bias_out + i, acc[i]);
+        }
+      } else if (colsum) {
         // thread m sums pixel row m (MODE 64) or rows (m & 63), (m & 63) + 64 of its 64-channel half (MODE 128)
         float acc[64];
 #pragma unroll
@@ -230,7 +293,10 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
       for (int g = 0; g < Cfg::GROUPS; ++g) {
         long row;
         bool valid = true;
-        if (MODE == 64) {
+        if (MODE == 32) {
+          valid = m < 96;  // the fourth 32-row block is the don't-care pixel
+          row = (long)(g * 3 + (m >> 5)) * p.cp_total + slab * 32 + (m & 31);
+        } else if (MODE == 64) {
           const int tap = m < 64 ? 2 * g : 2 * g + 1;
           valid = tap < 9;
           row = (long)tap * p.cp_total + slab * 64 + (m & 63);
@@ -281,7 +347,7 @@ int launch_hw_inst(HaloWgradParams& p, cudaStream_t stream) {
 }  // namespace
 
 int launch_halowgrad(HaloWgradParams& p, cudaStream_t stream) {
-  return p.mode == 64 ? launch_hw_inst<64>(p, stream) : launch_hw_inst<128>(p, stream);
+  return p.mode == 64 ? launch_hw_inst<64>(p, stream) : (p.mode == 32 ? launch_hw_inst<32>(p, stream) : launch_hw_inst<128>(p, stream));
 }
 
 }  // namespace refid

@@ -255,6 +255,8 @@ CASES = {
     "wgrad3x3_64_64": lambda: case_wgrad3x3(),
     "wgrad3x3_dual_64+64_64": lambda: case_wgrad3x3(cin2=64),
     "wgrad3x3_32_32": lambda: case_wgrad3x3(cin=32, cout=32),
+    "wgrad3x3_dual_32+32_32_ragged": lambda: case_wgrad3x3(cin=32, cin2=32, cout=32, H=40, W=20, N=3),
+    "wgrad3x3_32_32_many_tiles": lambda: case_wgrad3x3(cin=32, cout=32, H=64, W=96, N=4),
     "wgrad3x3_128_128": lambda: case_wgrad3x3(cin=128, cout=128, H=8, W=8),
     "wgrad3x3_256_256": lambda: case_wgrad3x3(cin=256, cout=256, H=8, W=8),
     "wgrad3x3_ragged": lambda: case_wgrad3x3(H=24, W=20, N=3),
