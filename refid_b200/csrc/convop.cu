@@ -315,7 +315,9 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
 
 // Returns 1 when lowered onto the halo-wgrad kernel, 0 when the op does not qualify, -1 on error.
 static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
-  if (d.kind != CK_3X3) return 0;
+  const bool down = d.kind == CK_DOWN4;
+  if (d.kind != CK_3X3 && !down) return 0;
+  if (down && (d.nsrc != 1 || d.src[0].C % 64 || (d.H & 1) || (d.W & 1) || q.C == 32)) return 0;
   for (int s = 0; s < d.nsrc; ++s)
     if (d.src[s].nmod) return 0;
   static const int disabled = getenv("REFID_NO_HALO_WGRAD") ? 1 : 0;
@@ -340,14 +342,16 @@ static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLa
   h.nsrc = d.nsrc;
   const int slab_c = mode == 32 ? 32 : 64;
   for (int s = 0; s < d.nsrc; ++s) h.src_slabs[s] = d.src[s].C / slab_c;
-  h.total_slabs = cp_total / slab_c;
+  h.total_slabs = (down ? 4 : 1) * (cp_total / slab_c);  // down: every parity view carries all Cin channels
+  h.down = down ? 1 : 0;
+  const int GH = down ? d.H / 2 : d.H, GW = down ? d.W / 2 : d.W;  // grid of the output gradient
   h.N = d.N;
-  h.H = d.H;
-  h.W = d.W;
-  h.tiles_x = (d.W + 7) / 8;
-  h.tiles_y = (d.H + 15) / 16;
+  h.H = GH;
+  h.W = GW;
+  h.tiles_x = (GW + 7) / 8;
+  h.tiles_y = (GH + 15) / 16;
   h.num_tiles = h.tiles_x * h.tiles_y * d.N;
-  h.jobs = mode == 128 ? (h.total_slabs / 2) * 3 * (q.C / 128) : h.total_slabs;
+  h.jobs = mode == 128 ? (h.total_slabs / 2) * (down ? 2 : 3) * (q.C / 128) : h.total_slabs;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -358,9 +362,15 @@ static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLa
   if (h.chunks < 1) h.chunks = 1;
   if (h.chunks > h.num_tiles) h.chunks = h.num_tiles;
   const int rows = mode == 128 ? 16 : 18;
-  for (int s = 0; s < d.nsrc; ++s)
-    if (make_act_map(&h.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, slab_c, 10, rows, 1)) return -1;
-  if (make_act_map(&h.tmQ, q.ptr, d.N, d.H, d.W, q.pitch, q.C, 0, 0, 1, slab_c, 8, 16, 1)) return -1;
+  if (down) {
+    for (int v = 0; v < 4; ++v)
+      if (make_act_map(&h.tmP[v], d.src[0].ptr, d.N, d.H, d.W, d.src[0].pitch, d.src[0].C, v >> 1, v & 1, 2, slab_c, 10, rows, 1))
+        return -1;
+  } else {
+    for (int s = 0; s < d.nsrc; ++s)
+      if (make_act_map(&h.tmP[s], d.src[s].ptr, d.N, d.H, d.W, d.src[s].pitch, d.src[s].C, 0, 0, 1, slab_c, 10, rows, 1)) return -1;
+  }
+  if (make_act_map(&h.tmQ, q.ptr, d.N, GH, GW, q.pitch, q.C, 0, 0, 1, slab_c, 8, 16, 1)) return -1;
   l->use_halo = 1;
   l->bias_done = d.bias_grad != nullptr;
   return 1;

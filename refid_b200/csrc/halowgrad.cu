@@ -16,6 +16,10 @@
 //            FOUR 32-row blocks one pixel (64 B) apart = the three dx taps of one kernel row + a don't-care block; one MMA
 //            group per dy, N = 32, 96 TMEM columns.
 //
+// The 4x4 stride-2 `down` conv (p.down) is the same kernel on the four stride-2 parity views of its input: view (py,px)
+// holds in[2i+py][2j+px] and contributes the taps dy in (py ? {-1,0} : {0,+1}), dx likewise -- 2 x 2 taps per view = the 16
+// kernel taps (ky = 2*dy + py + 1, kx = 2*dx + px + 1).  A slab's view index selects the tensor map and the tap set.
+//
 // Accumulation stays in TMEM over the CTA's whole pixel range (all T*B images of the batched launch); the fp32 result is
 // added to global memory once per CTA with vectorised reductions.
 #include "halowgrad.cuh"
@@ -86,19 +90,32 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
   const int t_begin = (int)(((long)p.num_tiles * chunk) / p.chunks);
   const int t_end = (int)(((long)p.num_tiles * (chunk + 1)) / p.chunks);
   int slab, dy = 0, coblk = 0;  // slab: global 64-channel slab index (MODE 64) or first slab of the pair (MODE 128)
+  const int ndy = p.down ? 2 : 3;  // kernel rows a MODE 128 job family covers
+  int dyi = 0;
   if (MODE == 64 || MODE == 32) {
     slab = job;
   } else {
     const int pairs = p.total_slabs / 2;
     slab = (job % pairs) * 2;
-    dy = (job / pairs) % 3 - 1;
-    coblk = job / (pairs * 3);
+    dyi = (job / pairs) % ndy;
+    dy = dyi - 1;
+    coblk = job / (pairs * ndy);
   }
-  const int src = slab >= p.src_slabs[0] ? 1 : 0;
-  const int slab_in_src = slab - (src ? p.src_slabs[0] : 0);
+  int src = slab >= p.src_slabs[0] ? 1 : 0;
+  int slab_in_src = slab - (src ? p.src_slabs[0] : 0);
+  // `down`: source = parity view of the slab; first tap offsets of the view in y / x (the second is +1)
+  int py = 0, px = 0;
+  if (p.down) {
+    src = slab / p.src_slabs[0];
+    slab_in_src = slab % p.src_slabs[0];
+    py = src >> 1;
+    px = src & 1;
+    dy = (py ? -1 : 0) + dyi;
+  }
+  const int dy0 = py ? -1 : 0, dx0 = px ? -1 : 0;
 
   // bias gradient: one job per Cout block also column-sums the G tiles it streams (4 extra arrivals free a stage)
-  const bool colsum = p.bias_out != nullptr && (MODE == 128 ? (slab == 0 && dy == -1) : job == 0);
+  const bool colsum = p.bias_out != nullptr && (MODE == 128 ? (slab == 0 && dyi == 0) : job == 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHWMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -171,6 +188,16 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
                 umma_bf16(tm + (uint32_t)(g * 32), ad, bd0 + (uint64_t)(ks * 64), IDESC, (it > 0 || ks > 0) ? 1u : 0u);
               }
             }
+          } else if (MODE == 64 && p.down) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {  // g = the view's kernel row; the two M halves are its two dx taps (one pixel apart)
+                const uint32_t offa = (uint32_t)((2 * ks + dy0 + g + 1) * (int)PITCH + dx0 + 1) * 128u;
+                const uint64_t ad = make_smem_desc(st + offa, 128u, SBO_A, 2u);
+                umma_bf16(tm + (uint32_t)(g * 64), ad, bd0 + (uint64_t)(ks * 128), IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
           } else if (MODE == 64) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
@@ -182,6 +209,16 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
                 const uint32_t lbo = g < 4 ? offb - offa : 128u;  // group 4: second half is a don't-care copy
                 const uint64_t ad = make_smem_desc(st + offa, lbo, SBO_A, 2u);
                 umma_bf16(tm + (uint32_t)(g * 64), ad, bd0 + (uint64_t)(ks * 128), IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+          } else if (p.down) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {  // the view's two dx taps
+                const uint32_t offa = (uint32_t)((2 * ks) * (int)PITCH + dx0 + g + 1) * 128u;
+                const uint64_t ad = make_smem_desc(st + offa, Cfg::P_BYTES, SBO_A, 2u);
+                umma_bf16(tm + (uint32_t)(g * 128), ad, bd0 + (uint64_t)(ks * 128), IDESC, (it > 0 || ks > 0) ? 1u : 0u);
               }
             }
           } else {
@@ -290,10 +327,15 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
       mbar_wait(acc_bar, 0, 0x820);
       tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < Cfg::GROUPS; ++g) {
+      for (int g = 0; g < (p.down ? 2 : Cfg::GROUPS); ++g) {
         long row;
         bool valid = true;
-        if (MODE == 32) {
+        if (p.down) {
+          // kernel tap of this accumulator row: MODE 64: row g of the view, dx half m >> 6; MODE 128: row dy, dx = g
+          const int ddy = MODE == 64 ? dy0 + g : dy, ddx = MODE == 64 ? dx0 + (m >> 6) : dx0 + g;
+          const int tap = (2 * ddy + py + 1) * 4 + (2 * ddx + px + 1);
+          row = (long)tap * p.cp_total + slab_in_src * 64 + (MODE == 64 ? (m & 63) : m);
+        } else if (MODE == 32) {
           valid = m < 96;  // the fourth 32-row block is the don't-care pixel
           row = (long)(g * 3 + (m >> 5)) * p.cp_total + slab * 32 + (m & 31);
         } else if (MODE == 64) {

@@ -5,11 +5,12 @@
 namespace refid {
 
 struct HaloWgradParams {
-  CUtensorMap tmP[2];  // conv input per source: dims (C, W, H, N), box (64, 10, 18 | 16, 1), 128B swizzle
+  CUtensorMap tmP[4];  // conv input per source (down: the four stride-2 parity views of the one source): dims (C, W, H, N), box (64, 10, 18 | 16, 1), 128B swizzle
   CUtensorMap tmQ;     // output gradient: dims (CQ, W, H, N), box (64, 8, 16, 1)
   float* out;          // [9 * cp_total][CQ] fp32, accumulated with reductions
   float* bias_out;     // optional [CQ] fp32: += column sums of the output gradient (bias gradient), computed from the G
                        // tiles in shared memory by the otherwise idle epilogue warps of one job per Cout block
+  int down;            // 4x4 stride-2 conv: sources = parity views, 2 x 2 taps per view (see halowgrad.cu)
   int mode;            // 64: Cout == 64; 128: Cout % 128 == 0 and every source a multiple of 128 channels
   int CQ, cp_total;
   int nsrc, src_slabs[2], total_slabs;

@@ -265,5 +265,8 @@ CASES = {
     "wgrad3x3_64_64_many_tiles": lambda: case_wgrad3x3(H=64, W=64, N=5),
     "wgrad1x1_128_64": lambda: case_wgrad1x1(),
     "wgrad_down4_64": lambda: case_wgrad_down4(),
+    "wgrad_down4_64_ragged": lambda: case_wgrad_down4(N=3, H=40, W=24),
+    "wgrad_down4_128": lambda: case_wgrad_down4(N=2, H=48, W=32, c=128),
+    "wgrad_down4_256": lambda: case_wgrad_down4(N=2, H=16, W=32, c=256),
     "wgrad_up2_128_64": lambda: case_wgrad_up2(),
 }
