@@ -443,17 +443,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           }
         };
         EpiPF fa, fb;  // two register sets, alternating: no copies
+        // the global operands do not depend on the accumulator: the first TWO groups are requested before the
+        // accumulator-ready wait, every later group two groups ahead of its use
         if (INPUTS && hsel < G) prefetch(hsel, fa);
+        if (INPUTS && hsel + 2 < G) prefetch(hsel + 2, fb);
         mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
         tc_fence_after();
         if (INPUTS) {
 #pragma unroll 1
           for (int g = hsel; g < G; g += 4) {
-            if (g + 2 < G) prefetch(g + 2, fb);
             process(g, fa);
+            if (g + 4 < G) prefetch(g + 4, fa);
             if (g + 2 < G) {
-              if (g + 4 < G) prefetch(g + 4, fa);
               process(g + 2, fb);
+              if (g + 6 < G) prefetch(g + 6, fb);
             }
           }
         } else {
