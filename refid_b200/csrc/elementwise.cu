@@ -326,9 +326,12 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __re
 #pragma unroll
     for (int t = 0; t < 9; ++t) aw[k][t] = 0.f;
   }
-  for (int j = 0; j < kDwBwdPix / 32; ++j) {
-    const long pix = (long)blockIdx.x * kDwBwdPix + j * 32 + pl;
-    if (pix >= npix) break;
+  // persistent blocks: the weight-gradient partials stay in registers over the block's whole pixel range, so every output
+  // address receives one atomic per BLOCK (<= #SMs) instead of one per 256 pixels (512 contended atomics per address)
+  for (long j = 0;; ++j) {
+    const long pix = ((long)blockIdx.x + j / (kDwBwdPix / 32) * gridDim.x) * kDwBwdPix + (j % (kDwBwdPix / 32)) * 32 + pl;
+    if (((long)blockIdx.x + j / (kDwBwdPix / 32) * gridDim.x) * kDwBwdPix >= npix) break;
+    if (pix >= npix) continue;
     const int n = (int)(pix / hw);
     const int y = (int)((pix % hw) / W), x = (int)(pix % W);
     // All 18 neighbour chunks are fetched unconditionally (clamped address, zero weight outside the image) and BEFORE any
@@ -666,7 +669,9 @@ int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __n
 int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* w, __nv_bfloat16* ga, float* gw, float* gb,
                   int N, int H, int W, cudaStream_t s) {
   const long npix = (long)N * H * W;
-  k_dw_bwd<<<blocks_for(npix, kDwBwdPix), kEwThreads, 0, s>>>(gd, a, w, ga, gw, gb, N, H, W);
+  unsigned blocks = blocks_for(npix, kDwBwdPix);
+  if (blocks > 148u) blocks = 148u;
+  k_dw_bwd<<<blocks, kEwThreads, 0, s>>>(gd, a, w, ga, gw, gb, N, H, W);
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
