@@ -111,8 +111,9 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     int c = groups[g].channels & -groups[g].channels;  // largest power of two dividing the group
     if (c < seg) seg = c;
   }
-  static const int bn_max = getenv("REFID_HALO_BNMAX") ? atoi(getenv("REFID_HALO_BNMAX")) : 256;
-  int BN = kc == 64 ? bn_max : 128;
+  // widest N tile that divides the output channels: measured on B200, 256 beats 128 even for the 64-tile bottleneck convs
+  // (the weight stream per pixel halves), and 128/64 splits of C = 256 layers were 20-80 % slower
+  int BN = kc == 64 ? 256 : 128;
   while (BN > 32 && total % BN) BN >>= 1;
   if (total % BN) return 0;
   if (seg > BN) seg = BN;
