@@ -88,8 +88,10 @@ static int make_patch_map(CUtensorMap* m, const ActSrc& s, int N, int H, int W, 
 static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLaunch* out) {
   const bool down_dgrad = d.kind == CK_DOWN4_DGRAD_HALO;
   const bool down_fwd = d.kind == CK_DOWN4_HALO;  // 3x3 over the four stride-2 parity views of the single source
-  if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad && !down_fwd) return 0;
-  if (down_dgrad && ngroups != 1) return 0;
+  const bool up2 = d.kind == CK_UP2;              // ConvTranspose 2x2 s2: a 1x1 conv whose four N blocks are the output parities
+  const bool scatter4 = down_dgrad || up2;        // four replicas of the output groups, scattered with stride 2
+  if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad && !down_fwd && !up2) return 0;
+  if (scatter4 && ngroups != 1) return 0;
   if (down_fwd && (d.nsrc != 1 || d.src[0].C % 64 || (d.H & 1) || (d.W & 1) || 4 * (d.src[0].C / 64) > 16)) return 0;
   const int GH = down_fwd ? d.H / 2 : d.H, GW = down_fwd ? d.W / 2 : d.W;  // grid the pixel tiles run over
   for (int g = 0; g < ngroups; ++g)  // GELU epilogues exist on the halo engine for 1x1 convs only (EGACA); else tap-GEMM
@@ -120,8 +122,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   if (BN % seg || (total / seg) > kMaxNBlocks) return 0;
   HaloConvParams& h = out->hp;
   memset(&h, 0, sizeof(h));
-  h.num_taps = d.kind == CK_1X1 ? 1 : 9;
-  h.halo = d.kind == CK_1X1 ? 0 : 1;
+  h.num_taps = (d.kind == CK_1X1 || up2) ? 1 : 9;
+  h.halo = (d.kind == CK_1X1 || up2) ? 0 : 1;
   h.pitch_px = h.halo ? 10 : 8;
   h.wrows_per_tap = d.wrows_per_tap;
   h.w_row0 = d.w_row0;
@@ -147,8 +149,8 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     }
     h.resident_tiles = tiles;
   }
-  h.n_blocks = (down_dgrad ? 4 : 1) * (total / BN);
-  if (h.n_blocks > kMaxNBlocks || (down_dgrad && 4 * (total / seg) > kMaxNBlocks)) return 0;
+  h.n_blocks = (scatter4 ? 4 : 1) * (total / BN);
+  if (h.n_blocks > kMaxNBlocks || (scatter4 && 4 * (total / seg) > kMaxNBlocks)) return 0;
   if (down_dgrad) {
     // N blocks enumerate (output parity q = qy*2+qx, channel block); parity q of dX[2i+qy][2j+qx] uses the taps (dy,dx) of
     // the dY neighbourhood with ky = qy + 1 - 2*dy and kx = qx + 1 - 2*dx inside the 4x4 kernel
@@ -198,16 +200,16 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   }
   if (make_mat_map(&h.tmB, d.w, d.w_rows, d.w_cols, kc, BN)) return -1;
   int nd = 0;
-  for (int q = 0; q < (down_dgrad ? 4 : 1); ++q)
+  for (int q = 0; q < (scatter4 ? 4 : 1); ++q)
     for (int g = 0; g < ngroups; ++g)
       for (int c = 0; c < groups[g].channels; c += seg) {
         EpiDesc e = groups[g].epi;
         e.coff += c;
-        e.osy = e.osx = down_dgrad ? 2 : 1;
-        e.ooy = down_dgrad ? (q >> 1) : 0;
-        e.oox = down_dgrad ? (q & 1) : 0;
-        e.OH = down_dgrad ? 2 * d.H : GH;
-        e.OW = down_dgrad ? 2 * d.W : GW;
+        e.osy = e.osx = scatter4 ? 2 : 1;
+        e.ooy = scatter4 ? (q >> 1) : 0;
+        e.oox = scatter4 ? (q & 1) : 0;
+        e.OH = scatter4 ? 2 * d.H : GH;
+        e.OW = scatter4 ? 2 * d.W : GW;
         h.epi[nd++] = e;
       }
   out->use_halo = 1;
