@@ -182,6 +182,13 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
+// gelu(x) and gelu'(x) from one erf evaluation
+__device__ __forceinline__ void gelu_both_f(float x, float* g, float* dg) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  *g = x * cdf;
+  *dg = cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -16,7 +16,7 @@ inline unsigned blocks_for(long n, int per_block) {
 
 __device__ __forceinline__ float act_mask(float sv, int act, float slope) {
   if (act == ACT_LRELU) return sv > 0.f ? 1.f : slope;
-  if (act == ACT_GELU) return gelu_grad_f(sv);
+  if (act == ACT_MULT) return sv;  // saved derivative (GELU layers)
   return 1.f;
 }
 
@@ -273,9 +273,10 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __re
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += ma[t] * v[k] * sw[(grp * 8 + k) * 9 + t];
     }
-    store8(d + (size_t)pix * 64 + grp * 8, acc);
+    float dg[8];  // the "pre-activation" buffer holds gelu'(z): the backward multiplies (ACT_MULT)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) gv[k] = gelu_f(acc[k]);
+    for (int k = 0; k < 8; ++k) gelu_both_f(acc[k], &gv[k], &dg[k]);
+    store8(d + (size_t)pix * 64 + grp * 8, dg);
     store8(g + (size_t)pix * 64 + grp * 8, gv);
   }
   if (pool) {
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(kEwThreads) k_gate_bwd_apply(const __nv_bfloat
     o[0] = f0;
     o[1] = f1;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) gb[k] = (gb[k] * sk[k] + __ldg(gp + k)) * gelu_grad_f(d[k]);
+    for (int k = 0; k < 8; ++k) gb[k] = (gb[k] * sk[k] + __ldg(gp + k)) * d[k];  // d = saved gelu'(z)
     store8(gz_de + i * 8, gb);
   }
 }

@@ -39,7 +39,7 @@ int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStrea
 int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bfloat16* add, __nv_bfloat16* dst, int dst_acc,
                   float* dstf, long npix, cudaStream_t s);
 
-// Depthwise 3x3 (pad 1) over C = 64: d = dw(a) + bias (saved pre-activation), g = GELU(d); pool[n][c] += sum_pix g.
+// Depthwise 3x3 (pad 1) over C = 64: z = dw(a) + bias, g = GELU(z), d = GELU'(z) (saved for the backward); pool[n][c] += sum_pix g.
 int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
                   int N, int H, int W, cudaStream_t s);
 // ga = dw^T(gd); gw[c][tap] += sum a[p+tap] gd[p]; gb[c] += sum gd[p].
@@ -69,7 +69,7 @@ int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const floa
 // gs[n][c] += sum_pix gcs[:, c]*gi + gcs[:, 64+c]*ge
 int launch_gate_bwd_reduce(const __nv_bfloat16* gcs, const __nv_bfloat16* gi, const __nv_bfloat16* ge, float* gs, int N,
                            long hw, cudaStream_t st);
-// gi_f32 += gcs[:, :64]*s ;  gz_de = (gcs[:, 64:]*s + gpool[n]) * gelu'(d_e)
+// gi_f32 += gcs[:, :64]*s ;  gz_de = (gcs[:, 64:]*s + gpool[n]) * d_e      (d_e = saved gelu'(z_e))
 int launch_gate_bwd_apply(const __nv_bfloat16* gcs, const float* s, const float* gpool, const __nv_bfloat16* d_e, float* gi_f32,
                           __nv_bfloat16* gz_de, int N, long hw, cudaStream_t st);
 

@@ -522,7 +522,7 @@ struct Engine {
       }
       if (tens[id].act != ACT_NONE) {
         a.sv = P(tens[id].mask_off);
-        a.act = tens[id].act;
+        a.act = tens[id].act == ACT_GELU ? ACT_MULT : tens[id].act;
         a.slope = tens[id].slope;
       }
       a.dst = P(tens[id].goff);
@@ -556,7 +556,7 @@ struct Engine {
     }
     if (tens[id].act != ACT_NONE) {
       t->sv = P(tens[id].mask_off);
-      t->act = tens[id].act;
+      t->act = tens[id].act == ACT_GELU ? ACT_MULT : tens[id].act;
       t->slope = tens[id].slope;
     }
     tens[id].gwritten = true;
@@ -603,7 +603,7 @@ struct Engine {
       a.f = PF(tens[id].gfoff);
       if (tens[id].act != ACT_NONE) {
         a.sv = P(tens[id].mask_off);
-        a.act = tens[id].act;
+        a.act = tens[id].act == ACT_GELU ? ACT_MULT : tens[id].act;
         a.slope = tens[id].slope;
       }
       a.dst = P(tens[id].goff);

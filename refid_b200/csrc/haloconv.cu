@@ -113,9 +113,9 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
     for (int k = 0; k < 4; ++k) {
       float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       add_chunk8(t, f.c[k]);
-      if (GELU && e.act == ACT_GELU) {
+      if (e.act == ACT_MULT) {  // saved derivative (GELU layers)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[8 * k + i] *= gelu_grad_f(t[i]);
+        for (int i = 0; i < 8; ++i) v[8 * k + i] *= t[i];
       } else {
         const float sl = e.slope;
 #pragma unroll
@@ -123,14 +123,22 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       }
     }
   } else {
-    if (e.out_pre) store32(e.out_pre + off, v);
-    if (e.act == ACT_LRELU) {
-      const float sl = e.slope;
+    if (GELU && e.act == ACT_GELU) {
+      // out = gelu(z); out_pre = gelu'(z) for the backward pass (chunk-wise: 8 temporaries)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
-    } else if (GELU && e.act == ACT_GELU) {
+      for (int k = 0; k < 4; ++k) {
+        float dg[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+        for (int i = 0; i < 8; ++i) gelu_both_f(v[8 * k + i], &v[8 * k + i], &dg[i]);
+        if (e.out_pre) store8(e.out_pre + off + 8 * k, dg);
+      }
+    } else {
+      if (e.out_pre) store32(e.out_pre + off, v);
+      if (e.act == ACT_LRELU) {
+        const float sl = e.slope;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+      }
     }
   }
   if (e.out_nchw && cseg == 0) {

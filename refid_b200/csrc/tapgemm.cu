@@ -54,23 +54,27 @@ __device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const fl
   if (e.sv) {
     float t[16];
     load16(e.sv + base + c0, t);
-    if (e.act == ACT_GELU) {
+    if (e.act == ACT_MULT) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= gelu_grad_f(t[i]);
+      for (int i = 0; i < 16; ++i) v[i] *= t[i];
     } else {
       const float sl = e.slope;
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] *= (t[i] > 0.f ? 1.f : sl);
     }
   } else {
-    if (e.out_pre) store16(e.out_pre + base + c0, v);
-    if (e.act == ACT_LRELU) {
-      const float sl = e.slope;
+    if (e.act == ACT_GELU) {
+      float dg[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
-    } else if (e.act == ACT_GELU) {
+      for (int i = 0; i < 16; ++i) gelu_both_f(v[i], &v[i], &dg[i]);
+      if (e.out_pre) store16(e.out_pre + base + c0, dg);
+    } else {
+      if (e.out_pre) store16(e.out_pre + base + c0, v);
+      if (e.act == ACT_LRELU) {
+        const float sl = e.slope;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+      }
     }
   }
   if (e.out) store16(e.out + base + c0, v);

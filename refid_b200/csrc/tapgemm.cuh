@@ -15,12 +15,14 @@ namespace refid {
 constexpr int kMaxTaps = 16;
 constexpr int kMaxNBlocks = 8;
 
-enum ActKind : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2 };
+// ACT_MULT: backward only -- the saved tensor already holds the activation's derivative (GELU layers store gelu'(z) next
+// to gelu(z) in the forward pass, so the backward multiplies instead of evaluating erf + exp per element again)
+enum ActKind : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_MULT = 3 };
 
 // Epilogue of one N block (all pointers share pixel mapping, channel pitch C and channel offset coff).
 //   a = acc + bias[n*bias_nstride + c] + pre + pre2
-//   if sv:  a *= act'(sv)      (LRELU: sv>0 ? 1 : slope, evaluated on the saved OUTPUT; GELU: on the saved PRE-activation)
-//   else :  if out_pre: out_pre = a;   a = act(a)
+//   if sv:  a *= act'(sv)      (LRELU: sv>0 ? 1 : slope, evaluated on the saved OUTPUT; MULT: a *= sv, sv = saved derivative)
+//   else :  if out_pre: out_pre = (act == GELU ? gelu'(a) : a);   a = act(a)
 //   out = a;  out_f32 += a;  out2 = a + post;  out_nchw[c < nchw_C] = a
 struct EpiDesc {
   __nv_bfloat16* out;
