@@ -529,7 +529,7 @@ struct Engine {
       a.dst_acc = tens[id].gwritten ? 1 : 0;
       a.n = tens[id].elems();
       tens[id].gwritten = true;
-      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, "addmask");
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, (std::string("addmask:flush") + ":" + std::to_string(tens[id].H) + "x" + std::to_string(tens[id].C)).c_str());
       gunref(g0);
       gunref(g1);
     }
@@ -575,7 +575,7 @@ struct Engine {
       a.dstf = PF(tens[id].gfoff);
       a.n = tens[id].elems();
       tens[id].gfwritten = true;
-      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, "addmask");
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, (std::string("addmask:f32acc") + ":" + std::to_string(tens[id].H) + "x" + std::to_string(tens[id].C)).c_str());
       return 0;
     }
     if (src_gidx >= 0) gbufs[src_gidx].refs++;
@@ -609,7 +609,7 @@ struct Engine {
       a.dst = P(tens[id].goff);
       a.n = tens[id].elems();
       tens[id].gwritten = true;
-      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, "addmask");
+      emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, (std::string("addmask:f32fin") + ":" + std::to_string(tens[id].H) + "x" + std::to_string(tens[id].C)).c_str());
       *gz = P(tens[id].goff);
       return 0;
     }
