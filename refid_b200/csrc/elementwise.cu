@@ -246,12 +246,16 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __re
   if (threadIdx.x < 64) sw[64 * 9 + threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const long hw = (long)H * W, npix = (long)N * hw;
-  const long pix = (long)blockIdx.x * 32 + pl;
+  const long hw = (long)H * W;
+  // blockIdx.y = sample, blockIdx.x = 32-pixel chunk of that sample: a block never straddles two samples, so the pooled
+  // sums can be written as per-block partials and reduced in a fixed order (bit-reproducible forward pass)
+  const long pin = (long)blockIdx.x * 32 + pl;
+  const bool inside = pin < hw;
+  const long pix = (long)blockIdx.y * hw + pin;
   float gv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (pix < npix) {
-    const int n = (int)(pix / hw);
-    const int y = (int)((pix % hw) / W), x = (int)(pix % W);
+  if (inside) {
+    const int n = (int)blockIdx.y;
+    const int y = (int)(pin / W), x = (int)(pin % W);
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = sw[64 * 9 + grp * 8 + k];
@@ -277,30 +281,23 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __re
     store8(d + (size_t)pix * 64 + grp * 8, dg);
     store8(g + (size_t)pix * 64 + grp * 8, gv);
   }
-  if (pool) {
-    const long first = (long)blockIdx.x * 32, last = min(first + 31, npix - 1);
-    if (first / hw == last / hw) {  // whole block inside one sample: block-level reduction
+  if (pool) {  // pool = per-block partial sums [N][gridDim.x][64]
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 8);
-        gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 16);
-      }
-      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      if (lane < 8) {
+    for (int k = 0; k < 8; ++k) {
+      gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 8);
+      gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 16);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) spool[warp][lane * 8 + k] = gv[k];
-      }
-      __syncthreads();
-      if (threadIdx.x < 64) {
-        float s = 0.f;
+      for (int k = 0; k < 8; ++k) spool[warp][lane * 8 + k] = gv[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float s = 0.f;
 #pragma unroll
-        for (int wq = 0; wq < 8; ++wq) s += spool[wq][threadIdx.x];
-        atomicAdd(pool + (first / hw) * 64 + threadIdx.x, s);
-      }
-    } else if (pix < npix) {
-      const int n = (int)(pix / hw);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(pool + (size_t)n * 64 + grp * 8 + k, gv[k]);
+      for (int wq = 0; wq < 8; ++wq) s += spool[wq][threadIdx.x];
+      pool[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + threadIdx.x] = s;
     }
   }
 }
@@ -406,11 +403,13 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __re
 // ---------------------------------------------------------------------------------------------
 // squeeze-excite MLP: one block of 64 threads per sample
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_se_fwd(const float* __restrict__ pool_sum, float inv_hw, SeParams p, float* s,
+__global__ void __launch_bounds__(64) k_se_fwd(const float* __restrict__ pool_part, int parts, float inv_hw, SeParams p, float* s,
                                                float* save_mean, float* save_z) {
   __shared__ float m[64], z[32];
   const int n = blockIdx.x, c = threadIdx.x;
-  m[c] = pool_sum[n * 64 + c] * inv_hw;
+  float sum = 0.f;  // fixed-order reduction of the depthwise kernel's per-block partial sums
+  for (int b = 0; b < parts; ++b) sum += pool_part[((size_t)n * parts + b) * 64 + c];
+  m[c] = sum * inv_hw;
   save_mean[n * 64 + c] = m[c];
   __syncthreads();
   if (c < 32) {
@@ -659,8 +658,8 @@ int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bf
 
 int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
                   int N, int H, int W, cudaStream_t s) {
-  const long npix = (long)N * H * W;
-  k_dw_fwd<<<blocks_for(npix, 32), kEwThreads, 0, s>>>(a, w, bias, d, g, pool, N, H, W);
+  dim3 grid(dw_pool_parts(H, W), N);
+  k_dw_fwd<<<grid, kEwThreads, 0, s>>>(a, w, bias, d, g, pool, N, H, W);
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -675,9 +674,9 @@ int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* 
   return 0;
 }
 
-int launch_se_fwd(const float* pool_sum, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
+int launch_se_fwd(const float* pool_part, int parts, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
                   cudaStream_t st) {
-  k_se_fwd<<<N, 64, 0, st>>>(pool_sum, inv_hw, p, s, save_mean, save_z);
+  k_se_fwd<<<N, 64, 0, st>>>(pool_part, parts, inv_hw, p, s, save_mean, save_z);
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -40,6 +40,8 @@ int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bf
                   float* dstf, long npix, cudaStream_t s);
 
 // Depthwise 3x3 (pad 1) over C = 64: z = dw(a) + bias, g = GELU(z), d = GELU'(z) (saved for the backward); pool[n][c] += sum_pix g.
+// pool (optional): per-block partial sums [N][dw_pool_parts(H, W)][64] fp32, reduced in fixed order by launch_se_fwd.
+inline int dw_pool_parts(int H, int W) { return (int)(((long)H * W + 31) / 32); }
 int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
                   int N, int H, int W, cudaStream_t s);
 // ga = dw^T(gd); gw[c][tap] += sum a[p+tap] gd[p]; gb[c] += sum gd[p].
@@ -57,7 +59,7 @@ struct SeParams {
   float* gw2;
   float* gb2;
 };
-int launch_se_fwd(const float* pool_sum, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
+int launch_se_fwd(const float* pool_part, int parts, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
                   cudaStream_t st);
 // gpool[n][c] = inv_hw * dL/dmean[n][c]
 int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const float* save_z, float inv_hw, SeParams p,

@@ -957,18 +957,12 @@ struct Engine {
     c1.in[0] = n_e;
     const int a_e = conv(c1);
     if (a_e < 0) return -1;
-    // small fp32 state: pooled sums, gate, saved mean / hidden, and their gradients
+    // small fp32 state: gate, saved mean / hidden, and their gradients; per-block partial sums of the global pool
+    const int parts = dw_pool_parts(te.H, te.W);
     const long small = act_alloc((size_t)N * (64 * 5 + 32) * 4);
-    const long pool_off = small, s_off = small + N * 64 * 4, mean_off = small + N * 128 * 4, gs_off = small + N * 192 * 4,
+    const long s_off = small + N * 64 * 4, mean_off = small + N * 128 * 4, gs_off = small + N * 192 * 4,
                gpool_off = small + N * 256 * 4, z_off = small + N * 320 * 4;
-    {
-      char* p = ws + pool_off;
-      const size_t n = (size_t)N * 64 * 4;
-      emit([p, n](cudaStream_t st) {
-        REFID_CUDA_CHECK(cudaMemsetAsync(p, 0, n, st));
-        return 0;
-      });
-    }
+    const long pool_off = act_alloc((size_t)N * parts * 64 * 4);
     const int g_e = dw(a_e, site(a + ".conv2_e"), pool_off, nm + ".g_e");
     const int s1 = site(a + ".se_1.1"), s2 = site(a + ".se_1.3");
     if (s1 < 0 || s2 < 0) return -1;
@@ -987,7 +981,7 @@ struct Engine {
       float *pool = PF(pool_off), *sg = PF(s_off), *mean = PF(mean_off), *z = PF(z_off);
       const __nv_bfloat16 *pgi = P(tens[g_i].off), *pge = P(tens[g_e].off);
       __nv_bfloat16* pcs = P(tens[cs].off);
-      emit([pool, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, inv_hw, sp, sg, mean, z, N, st); }, LC_OTHER, 0.0, "se_fwd");
+      emit([pool, parts, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, parts, inv_hw, sp, sg, mean, z, N, st); }, LC_OTHER, 0.0, "se_fwd");
       emit([pgi, pge, sg, pcs, N, hw](cudaStream_t st) { return launch_gate_fwd(pgi, pge, sg, pcs, N, hw, st); }, LC_OTHER, 0.0, "gate_fwd");
     }
     if (train) {
