@@ -22,6 +22,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-o", OUT, SRC]
+    cmd[1:1] = os.environ.get("REFID_NVCC_FLAGS", "").split()  # diagnostic builds, e.g. -DREFID_HALO_TIMING
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -97,6 +97,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   }
 }
 
+// Stage cursor of a ring of `n` mbarrier-guarded buffers: stage index + phase bit, advanced without integer division
+// (the stage count is a run-time launch parameter; a `%`/`/` by it is ~25 dependent instructions, and the tcgen05 queue
+// is shallow enough that instructions between MMAs of the issuing thread show up as tensor-pipe idle time).
+struct RingPos {
+  uint32_t s = 0, ph = 0;
+  __device__ __forceinline__ void advance(uint32_t n) {
+    if (++s == n) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+};
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }

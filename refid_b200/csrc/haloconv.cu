@@ -5,6 +5,17 @@
 #include <stdlib.h>
 
 namespace refid {
+#ifdef REFID_HALO_TIMING
+__device__ long long g_halo_t[148 * 8];
+#define HT_DECL long long ht_acc = 0, ht_a = 0, ht_b = 0, ht_mma = 0, ht_t0 = clock64(), ht_x
+#define HT_BEGIN ht_x = clock64()
+#define HT_END(v) v += clock64() - ht_x
+#else
+#define HT_DECL
+#define HT_BEGIN
+#define HT_END(v)
+#endif
+
 
 namespace {
 
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           }
       }
     }
-    uint32_t ia = 0, ib = 0;
+    RingPos ra, rb;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
       const int x0 = (tile % p.tiles_x) * 8;
@@ -266,24 +277,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
       int ks = 0;
       for (int src = 0; src < p.nsrc; ++src) {
         for (int slab = 0; slab < p.src_slabs[src]; ++slab, ++ks) {
-          const int sa = ia % SA;
-          mbar_wait(&a_empty[sa], ((ia / SA) & 1) ^ 1, 0x700 + sa);
+          const int sa = ra.s;
+          mbar_wait(&a_empty[sa], ra.ph ^ 1u, 0x700 + sa);
           if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[sa], A_TX);
             tma_load_4d(a_base + (size_t)sa * A_BYTES, &p.tmA[src], &a_full[sa], slab * KC, x0 - HALO, y0 - HALO, n);
           }
-          ++ia;
+          ra.advance(SA);
           if (!p.resident_b) {
             const unsigned tmask = (p.tap_mask[nblk] ? p.tap_mask[nblk] : 0xFFFFu) & (p.slab_mask[ks] ? p.slab_mask[ks] : 0xFFFFu);
             for (int tap = 0; tap < TAPS; ++tap) {
               if (!((tmask >> tap) & 1u)) continue;
-              const int sb = ib % SB;
-              mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1, 0x710 + sb);
+              const int sb = rb.s;
+              mbar_wait(&b_empty[sb], rb.ph ^ 1u, 0x710 + sb);
               if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[sb], B_TILE);
                 tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * KC, p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
               }
-              ++ib;
+              rb.advance(SB);
             }
           }
         }
@@ -297,17 +308,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
       tc_fence_after();
     }
     const uint32_t a_base_u = smem_u32(a_base), b_base_u = smem_u32(b_base);
-    uint32_t ia = 0, ib = 0, it = 0;
+    RingPos ra, rb;
+    uint32_t it = 0;
+    HT_DECL;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
       const unsigned nmask = p.tap_mask[item % p.n_blocks] ? p.tap_mask[item % p.n_blocks] : 0xFFFFu;
       bool first = true;  // the first MMA of the item overwrites the accumulator
+      HT_BEGIN;
       mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 0x730 + buf);
+      HT_END(ht_acc);
       tc_fence_after();
       const uint32_t acc = tm + buf * ACC_COLS;
       for (int ks = 0; ks < total_slabs; ++ks) {
-        const int sa = ia % SA;
-        mbar_wait(&a_full[sa], (ia / SA) & 1, 0x740 + sa);
+        const int sa = ra.s;
+        HT_BEGIN;
+        mbar_wait(&a_full[sa], ra.ph, 0x740 + sa);
+        HT_END(ht_a);
         tc_fence_after();
         const uint64_t a_desc0 = make_smem_desc(a_base_u + (uint32_t)sa * A_BYTES, 16, SBO, SWZ);
         const unsigned tmask = nmask & (p.slab_mask[ks] ? p.slab_mask[ks] : 0xFFFFu);
@@ -358,16 +375,65 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
             umma_commit(&a_empty[sa]);
           }
           __syncwarp();
+        } else if (TAPS == 9 && BN < 256 && (tmask & 0x1FFu) == 0x1FFu) {
+          // streamed weights, all nine taps: one issue block per kernel row (three weight stages, 3*NM*KSTEPS MMAs).  The
+          // tcgen05 queue is about one MMA deep, so every instruction the issuing thread spends between MMAs is tensor-pipe
+          // idle time: the three barrier probes are issued together (their latencies overlap), all descriptors are
+          // `stage base + constant`, and the per-block overhead (probe, elect, commit, warp sync) is paid once per 3 taps.
+#pragma unroll
+          for (int row = 0; row < 3; ++row) {
+            RingPos r0 = rb, r1 = rb;
+            r1.advance(SB);
+            RingPos r2 = r1;
+            r2.advance(SB);
+            HT_BEGIN;
+            const bool ok0 = mbar_try_wait(&b_full[r0.s], r0.ph);
+            const bool ok1 = mbar_try_wait(&b_full[r1.s], r1.ph);
+            const bool ok2 = mbar_try_wait(&b_full[r2.s], r2.ph);
+            if (!ok0) mbar_wait(&b_full[r0.s], r0.ph, 0x750 + r0.s);
+            if (!ok1) mbar_wait(&b_full[r1.s], r1.ph, 0x750 + r1.s);
+            if (!ok2) mbar_wait(&b_full[r2.s], r2.ph, 0x750 + r2.s);
+            HT_END(ht_b);
+            const uint64_t bdq[3] = {make_smem_desc(b_base_u + r0.s * B_TILE, 16, SBO_B, SWZ),
+                                     make_smem_desc(b_base_u + r1.s * B_TILE, 16, SBO_B, SWZ),
+                                     make_smem_desc(b_base_u + r2.s * B_TILE, 16, SBO_B, SWZ)};
+            uint64_t* const eq[3] = {&b_empty[r0.s], &b_empty[r1.s], &b_empty[r2.s]};
+            HT_BEGIN;
+            if (elect_one()) {
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const uint32_t tap_off = (uint32_t)(row * PITCH + q) * PXB;
+#pragma unroll
+                for (int j = 0; j < NM; ++j) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    const uint64_t ad = a_desc0 + (uint64_t)((tap_off + (uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
+                    const uint64_t bd = bdq[q] + (uint64_t)(((uint32_t)k * 32u) >> 4);
+                    umma_bf16(acc + j * BN, ad, bd, IDESC, (!first || row > 0 || q > 0 || k > 0) ? 1u : 0u);
+                  }
+                }
+                umma_commit(eq[q]);
+              }
+              if (row == 2) umma_commit(&a_empty[sa]);
+            }
+            __syncwarp();
+            HT_END(ht_mma);
+            rb = r2;
+            rb.advance(SB);
+          }
+          first = false;
         } else {
 #pragma unroll 1
           for (int tap = 0; tap < TAPS; ++tap) {
             if (!((tmask >> tap) & 1u)) continue;
-            const int sb = ib % SB;
-            mbar_wait(&b_full[sb], (ib / SB) & 1, 0x750 + sb);
-            tc_fence_after();
+            const int sb = rb.s;
+            HT_BEGIN;
+            mbar_wait(&b_full[sb], rb.ph, 0x750 + sb);
+            HT_END(ht_b);
             const uint32_t tap_off = (uint32_t)((TAPS == 9 ? tap / 3 : 0) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * PXB;
             const uint64_t a_desc = a_desc0 + (uint64_t)(tap_off >> 4);
             const uint64_t b_desc = make_smem_desc(b_base_u + (uint32_t)sb * B_TILE, 16, SBO_B, SWZ);
+            HT_BEGIN;
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
@@ -381,17 +447,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
               umma_commit(&b_empty[sb]);
             }
             __syncwarp();
+            HT_END(ht_mma);
             first = false;
-            ++ib;
+            rb.advance(SB);
           }
           if (elect_one()) umma_commit(&a_empty[sa]);
           __syncwarp();
         }
-        ++ia;
+        ra.advance(SA);
       }
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
+#ifdef REFID_HALO_TIMING
+    if (lane == 0 && blockIdx.x < 148) {
+      long long* o = g_halo_t + blockIdx.x * 8;
+      o[0] = clock64() - ht_t0; o[1] = ht_acc; o[2] = ht_a; o[3] = ht_b; o[4] = ht_mma; o[5] = it;
+    }
+#endif
   } else {
     // ---------------- epilogue: TMEM -> registers -> global, overlapped with the next item's MMAs ----------------
     const int q = warp & 3;  // TMEM lane quarter this warp may access (hardware rule: lanes 32*(warp%4)..+31)

@@ -142,12 +142,13 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
         tma_prefetch_desc(&p.tmQ);
       }
       int it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
+      RingPos ring;
+      for (int t = t_begin; t < t_end; ++t, ++it, ring.advance(S)) {
         const int x0 = (t % p.tiles_x) * 8;
         const int y0 = ((t / p.tiles_x) % p.tiles_y) * 16;
         const int n = t / tiles_per_img;
-        const int s = it % S;
-        mbar_wait(&empty_bar[s], ((it / S) & 1) ^ 1, 0x800 + s);
+        const int s = (int)ring.s;
+        mbar_wait(&empty_bar[s], ring.ph ^ 1u, 0x800 + s);
         if (elect_one()) {
           uint8_t* st = smem + (size_t)s * Cfg::STAGE;
           mbar_arrive_expect_tx(&full_bar[s], Cfg::TX);
@@ -170,9 +171,10 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
       constexpr uint32_t PXB = MODE == 32 ? 64u : 128u;  // bytes per pixel row of a slab
       constexpr uint32_t SBO_A = PITCH * PXB;          // next 8-pixel K group = next tile row of the patch
       int it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int s = it % S;
-        mbar_wait(&full_bar[s], (it / S) & 1, 0x810 + s);
+      RingPos ring;
+      for (int t = t_begin; t < t_end; ++t, ++it, ring.advance(S)) {
+        const int s = (int)ring.s;
+        mbar_wait(&full_bar[s], ring.ph, 0x810 + s);
         tc_fence_after();
         const uint32_t st = smem_u + (uint32_t)s * Cfg::STAGE;
         // B: G tile [128 px][64 co] per half; K step = 16 pixel rows of 128 B = 2048 B; halves 16 KB apart
@@ -247,10 +249,10 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = 0.f;
         const uint32_t smem_u = smem_u32(smem);
-        int it = 0;
-        for (int t = t_begin; t < t_end; ++t, ++it) {
-          const int s = it % S;
-          mbar_wait(&full_bar[s], (it / S) & 1, 0x830 + s);
+        RingPos ring;
+        for (int t = t_begin; t < t_end; ++t, ring.advance(S)) {
+          const int s = (int)ring.s;
+          mbar_wait(&full_bar[s], ring.ph, 0x830 + s);
           const uint32_t gt = smem_u + (uint32_t)s * Cfg::STAGE + Cfg::P_ALLOC;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -285,10 +287,10 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = 0.f;
         const uint32_t smem_u = smem_u32(smem);
-        int it = 0;
-        for (int t = t_begin; t < t_end; ++t, ++it) {
-          const int s = it % S;
-          mbar_wait(&full_bar[s], (it / S) & 1, 0x830 + s);
+        RingPos ring;
+        for (int t = t_begin; t < t_end; ++t, ring.advance(S)) {
+          const int s = (int)ring.s;
+          mbar_wait(&full_bar[s], ring.ph, 0x830 + s);
           const uint32_t gt = smem_u + (uint32_t)s * Cfg::STAGE + Cfg::P_ALLOC + (MODE == 128 ? (uint32_t)(m >> 6) * 16384u : 0u);
 #pragma unroll
           for (int rr = 0; rr < (MODE == 128 ? 2 : 1); ++rr) {

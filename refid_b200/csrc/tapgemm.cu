@@ -157,13 +157,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   if (warp == 0) {
     // TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues.
     if (elect_one()) tma_prefetch_desc(&p.tmB);
-    int it = 0;
+    RingPos ring;
     int kglob = 0;
     for (int src = 0; src < p.nsrc; ++src) {
       for (int slab = 0; slab < p.src_slabs[src]; ++slab, kglob += BK) {
-        for (int tap = 0; tap < p.num_taps; ++tap, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
+        for (int tap = 0; tap < p.num_taps; ++tap, ring.advance(S)) {
+          const int s = (int)ring.s;
+          const uint32_t ph = ring.ph;
           mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + s);
           if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -180,9 +180,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     // MMA issuer: uniform loop, elected lane issues; descriptors are `stage base + constant`.
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_u = smem_u32(smem);
-    for (int it = 0; it < total_iters; ++it) {
-      const int s = it % S;
-      const uint32_t ph = (it / S) & 1;
+    RingPos ring;
+    for (int it = 0; it < total_iters; ++it, ring.advance(S)) {
+      const int s = (int)ring.s;
+      const uint32_t ph = ring.ph;
       mbar_wait(&full_bar[s], ph, 0x200 + s);
       tc_fence_after();
       const uint32_t a_addr = smem_u + (uint32_t)s * STAGE_BYTES;

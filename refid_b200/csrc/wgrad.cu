@@ -54,15 +54,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   if (my_tiles > 0 && my_mt > 0) {
     if (warp == 0) {
       // TMA producer: uniform loop, one elected lane issues
-      int it = 0;
+      RingPos ring;
       for (int pt = blockIdx.x; pt < p.num_tiles; pt += gridDim.x) {
         const int tx_i = pt % p.tiles_x;
         const int ty_i = (pt / p.tiles_x) % p.tiles_y;
         const int tn_i = pt / (p.tiles_x * p.tiles_y);
         const int x0 = tx_i * p.TW, y0 = ty_i * p.TH, n0 = tn_i * p.TN;
-        for (int mt = 0; mt < my_mt; ++mt, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
+        for (int mt = 0; mt < my_mt; ++mt, ring.advance(S)) {
+          const int s = (int)ring.s;
+          const uint32_t ph = ring.ph;
           mbar_wait(&empty_bar[s], ph ^ 1, 0x400 + s);
           const int b0 = (mt0 + mt) * bpt;
           int nvalid = total_blocks - b0;
@@ -100,11 +100,11 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
       const uint32_t lboP = 128u * p.CB * 2u, sboP = 8u * p.CB * 2u;
       const uint32_t lboQ = 128u * p.CBq * 2u, sboQ = 8u * p.CBq * 2u;
       const uint64_t kstepP = (uint64_t)((16u * p.CB * 2u) >> 4), kstepQ = (uint64_t)((16u * p.CBq * 2u) >> 4);
-      int it = 0;
+      RingPos ring;
       for (int t = 0; t < my_tiles; ++t) {
-        for (int mt = 0; mt < my_mt; ++mt, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
+        for (int mt = 0; mt < my_mt; ++mt, ring.advance(S)) {
+          const int s = (int)ring.s;
+          const uint32_t ph = ring.ph;
           mbar_wait(&full_bar[s], ph, 0x500 + s);
           tc_fence_after();
           const uint32_t p_addr = smem_u + (uint32_t)s * STAGE_BYTES;

@@ -44,6 +44,12 @@ def bench(cin, cout, H, W, N, cin2=0, pre=False, reps=20):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     fl = 2.0 * N * H * W * 9 * (cin + cin2) * cout
+    if hasattr(L, "refid_debug_halo_timing"):
+        buf = (ctypes.c_longlong * (148 * 8))()
+        L.refid_debug_halo_timing(buf)
+        rows = [buf[i * 8:i * 8 + 6] for i in range(148)]
+        worst = max(rows, key=lambda r: r[0])
+        print("   MMA warp cycles (slowest CTA): total %d, acc_empty wait %d, A wait %d, B wait %d, issue blocks %d, items %d" % tuple(worst))
     print(f"cin {cin}+{cin2} cout {cout} {N}x{H}x{W} pre={pre}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF/s  (device time, CUDA-graph replay)", flush=True)
 
 print("REFID_HALO_DBG =", os.environ.get("REFID_HALO_DBG"))

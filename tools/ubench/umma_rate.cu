@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128, 1) k_rate(int M, int N, int iters, int a_
       }
     }
     umma_commit(&bar);
-    mbar_wait(&bar, 0, 1);
+    while (!mbar_try_wait(&bar, 0)) {}
     long long t1 = clock64();
     out[blockIdx.x] = t1 - t0;
   }
@@ -50,6 +50,20 @@ int main() {
     double ideal = (M < 128 ? 128 : M) * (double)N / 256.0;
     printf("M=%3d N=%3d: %.1f cyc/MMA (floor %.0f) eff %.2f  flop/clk/SM %.0f  %s\n", M, N, cyc, ideal, ideal * (M / 128.0) / cyc * (M<128?1:1),
            2.0 * M * N * 16 / cyc, cudaGetErrorString(e));
+  }
+  printf("--- sustained runs: SM cycles per MMA and wall time (clock under load) ---\n");
+  for (int N : {64, 128, 256}) {
+    const int iters = 400000;  // x4 MMAs
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k_rate<<<148, 128, 201 * 1024 + 1024>>>(128, N, iters, 16384, 16384, d, 0, 1024);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("N=%3d sustained: %.1f cyc/MMA, %.2f ms wall -> effective SM clock %.0f MHz, %.0f TFLOP/s  %s\n", N, (double)mx / (iters * 4.0), ms,
+           mx / (ms * 1e3), 2.0 * 128 * N * 16 * iters * 4.0 * 148 / (ms * 1e-3) / 1e12, cudaGetErrorString(e));
   }
   printf("--- A operand start offset / SBO variants (M=128) ---\n");
   int offs[] = {0, 128, 256, 512, 1152}; int sbos[] = {1024, 1280, 1152};
