@@ -1,6 +1,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace refid {
@@ -14,6 +15,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("REFID_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 
 int read_and_clear_abort_flag(cudaStream_t stream, unsigned int* out) {

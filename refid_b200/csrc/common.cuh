@@ -49,6 +49,32 @@ int make_mat_map(CUtensorMap* m, const void* base, long rows, long cols, int box
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the plan is launched with stream serialization relaxed, signals its
+// dependents at its first instruction and waits for its predecessor right after its own set-up (barrier init, TMEM
+// allocation), so launch latency, CTA scheduling and kernel prologues overlap the tail of the kernel before.  Rules kept
+// by every kernel: (1) pdl_wait() is executed by EVERY thread of EVERY CTA before it returns (a grid whose CTAs all
+// skipped the wait would complete early and unblock ITS dependents while the grid before is still running);
+// (2) nothing before pdl_wait() reads or writes global memory another kernel touches.  REFID_PDL=0 disables it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -25,6 +25,8 @@ __device__ __forceinline__ float act_mask(float sv, int act, float slope) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
                                                         int T, int Cin, int H, int W, int Kp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int G = Kp / 8;
   const long total = (long)B * T * H * G * W;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict_
 
 __global__ void __launch_bounds__(kEwThreads) k_gout_pack(const float* __restrict__ gout, __nv_bfloat16* __restrict__ out, int B,
                                                           int T, int Cv, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)B * T * H * W;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const long hw = (long)H * W;
@@ -73,6 +77,8 @@ __global__ void __launch_bounds__(kEwThreads) k_gout_pack(const float* __restric
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_colsum(const __nv_bfloat16* __restrict__ in, long rows, int C,
                                                        float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[kEwThreads][9];
   const int G = C / 8;                 // vector groups per row (4..32)
   const int lanes = kEwThreads / G;    // row lanes per block
@@ -101,6 +107,8 @@ __global__ void __launch_bounds__(kEwThreads) k_colsum(const __nv_bfloat16* __re
 // masked accumulate
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_addmask(const AddMaskArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long n8 = p.n / 8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -167,6 +175,8 @@ __device__ __forceinline__ void ln_stats(const float* x, float& mu, float& rstd)
 
 __global__ void __launch_bounds__(kEwThreads) k_ln_fwd(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                        long npix) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long nvec = npix * 8;
   const long iters = (nvec + (long)gridDim.x * blockDim.x - 1) / ((long)gridDim.x * blockDim.x);
   for (long it = 0; it < iters; ++it) {  // uniform trip count: shuffles need whole warps
@@ -185,6 +195,8 @@ __global__ void __launch_bounds__(kEwThreads) k_ln_fwd(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(kEwThreads) k_ln_bwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy,
                                                        const __nv_bfloat16* __restrict__ add, __nv_bfloat16* dst, int dst_acc,
                                                        float* dstf, long npix) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long nvec = npix * 8;
   const long iters = (nvec + (long)gridDim.x * blockDim.x - 1) / ((long)gridDim.x * blockDim.x);
   for (long it = 0; it < iters; ++it) {
@@ -240,6 +252,8 @@ __global__ void __launch_bounds__(kEwThreads) k_ln_bwd(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ d,
                                                        __nv_bfloat16* __restrict__ g, float* pool, int N, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sw[64 * 9 + 64];
   __shared__ float spool[8][64];
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
@@ -307,6 +321,8 @@ constexpr int kDwBwdPix = 256;  // pixels per block in the backward kernel (8 pe
 __global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __restrict__ gd, const __nv_bfloat16* __restrict__ a,
                                                        const float* __restrict__ w, __nv_bfloat16* __restrict__ ga, float* gw,
                                                        float* gb, int N, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sw[64 * 9];
   __shared__ float sred[64 * 10];
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
@@ -405,6 +421,8 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_se_fwd(const float* __restrict__ pool_part, int parts, float inv_hw, SeParams p, float* s,
                                                float* save_mean, float* save_z) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float m[64], z[32];
   const int n = blockIdx.x, c = threadIdx.x;
   float sum = 0.f;  // fixed-order reduction of the depthwise kernel's per-block partial sums
@@ -427,6 +445,8 @@ __global__ void __launch_bounds__(64) k_se_fwd(const float* __restrict__ pool_pa
 __global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, const float* __restrict__ s,
                                                const float* __restrict__ save_mean, const float* __restrict__ save_z, float inv_hw,
                                                SeParams p, float* gpool) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float gq[64], gz[32], m[64], z[32];
   const int n = blockIdx.x, c = threadIdx.x;
   const float sv = s[n * 64 + c];
@@ -456,6 +476,8 @@ __global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, con
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_gate_fwd(const __nv_bfloat16* __restrict__ gi, const __nv_bfloat16* __restrict__ ge,
                                                          const float* __restrict__ s, __nv_bfloat16* __restrict__ cs, int N, long hw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long nvec = (long)N * hw * 8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     const long pix = i >> 3;
@@ -481,6 +503,8 @@ constexpr int kGatePix = 512;  // pixels per block in the reduction (16 per thre
 __global__ void __launch_bounds__(kEwThreads) k_gate_bwd_reduce(const __nv_bfloat16* __restrict__ gcs,
                                                                 const __nv_bfloat16* __restrict__ gi,
                                                                 const __nv_bfloat16* __restrict__ ge, float* gs, long hw) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sred[64];
   if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
   __syncthreads();
@@ -516,6 +540,8 @@ __global__ void __launch_bounds__(kEwThreads) k_gate_bwd_apply(const __nv_bfloat
                                                                const float* __restrict__ gpool,
                                                                const __nv_bfloat16* __restrict__ d_e, float* gi_f32,
                                                                __nv_bfloat16* __restrict__ gz_de, int N, long hw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long nvec = (long)N * hw * 8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
     const long pix = i >> 3;
@@ -547,6 +573,8 @@ __global__ void __launch_bounds__(kEwThreads) k_gate_bwd_apply(const __nv_bfloat
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ flat, __nv_bfloat16* __restrict__ wpack,
                                                      const PackDesc* __restrict__ descs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const PackDesc d = descs[blockIdx.y];
   const long per_tap = (long)d.R * d.Cc;
   const long total = per_tap * d.ntaps;
@@ -580,7 +608,7 @@ int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, i
   const long total = (long)B * T * H * W * (Kp / 8);
   unsigned blocks = blocks_for(total, kEwThreads);
   if (blocks > 148u * 32u) blocks = 148u * 32u;
-  k_unroll5<<<blocks, kEwThreads, 0, s>>>(in, out, B, T, Cin, H, W, Kp);
+  REFID_CUDA_CHECK(launch_k(k_unroll5, dim3(blocks), dim3(kEwThreads), 0, s, in, out, B, T, Cin, H, W, Kp));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -590,7 +618,7 @@ int launch_gout_pack(const float* gout, __nv_bfloat16* out, int B, int T, int Cv
   const long total = (long)B * T * H * W;
   unsigned blocks = blocks_for(total, kEwThreads);
   if (blocks > 148u * 32u) blocks = 148u * 32u;
-  k_gout_pack<<<blocks, kEwThreads, 0, s>>>(gout, out, B, T, Cv, H, W);
+  REFID_CUDA_CHECK(launch_k(k_gout_pack, dim3(blocks), dim3(kEwThreads), 0, s, gout, out, B, T, Cv, H, W));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -600,13 +628,15 @@ int launch_colsum(const __nv_bfloat16* in, long rows, int C, float* out, cudaStr
   const int lanes = kEwThreads / (C / 8);
   unsigned blocks = blocks_for(rows, lanes * 16);
   if (blocks > 148u * 4u) blocks = 148u * 4u;
-  k_colsum<<<blocks, kEwThreads, 0, s>>>(in, rows, C, out);
+  REFID_CUDA_CHECK(launch_k(k_colsum, dim3(blocks), dim3(kEwThreads), 0, s, in, rows, C, out));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 __global__ void __launch_bounds__(kEwThreads) k_sum_series(const __nv_bfloat16* __restrict__ base, long slot_elems, int T,
                                                            __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long n8 = slot_elems / 8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -625,7 +655,7 @@ int launch_sum_series(const __nv_bfloat16* base, long slot_elems, int T, __nv_bf
   REFID_REQUIRE(slot_elems % 8 == 0, "sum_series: slot_elems=%ld not a multiple of 8", slot_elems);
   unsigned blocks = blocks_for(slot_elems / 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_sum_series<<<blocks, kEwThreads, 0, s>>>(base, slot_elems, T, out);
+  REFID_CUDA_CHECK(launch_k(k_sum_series, dim3(blocks), dim3(kEwThreads), 0, s, base, slot_elems, T, out));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -634,7 +664,7 @@ int launch_addmask(const AddMaskArgs& a, cudaStream_t s) {
   REFID_REQUIRE(a.n % 8 == 0, "addmask: n=%ld not a multiple of 8", a.n);
   unsigned blocks = blocks_for(a.n / 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_addmask<<<blocks, kEwThreads, 0, s>>>(a);
+  REFID_CUDA_CHECK(launch_k(k_addmask, dim3(blocks), dim3(kEwThreads), 0, s, a));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -642,7 +672,7 @@ int launch_addmask(const AddMaskArgs& a, cudaStream_t s) {
 int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s) {
   unsigned blocks = blocks_for(npix * 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_ln_fwd<<<blocks, kEwThreads, 0, s>>>(x, y, npix);
+  REFID_CUDA_CHECK(launch_k(k_ln_fwd, dim3(blocks), dim3(kEwThreads), 0, s, x, y, npix));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -651,7 +681,7 @@ int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bf
                   float* dstf, long npix, cudaStream_t s) {
   unsigned blocks = blocks_for(npix * 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_ln_bwd<<<blocks, kEwThreads, 0, s>>>(x, gy, add, dst, dst_acc, dstf, npix);
+  REFID_CUDA_CHECK(launch_k(k_ln_bwd, dim3(blocks), dim3(kEwThreads), 0, s, x, gy, add, dst, dst_acc, dstf, npix));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -659,7 +689,7 @@ int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bf
 int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
                   int N, int H, int W, cudaStream_t s) {
   dim3 grid(dw_pool_parts(H, W), N);
-  k_dw_fwd<<<grid, kEwThreads, 0, s>>>(a, w, bias, d, g, pool, N, H, W);
+  REFID_CUDA_CHECK(launch_k(k_dw_fwd, dim3(grid), dim3(kEwThreads), 0, s, a, w, bias, d, g, pool, N, H, W));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -669,21 +699,21 @@ int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* 
   const long npix = (long)N * H * W;
   unsigned blocks = blocks_for(npix, kDwBwdPix);
   if (blocks > 148u) blocks = 148u;
-  k_dw_bwd<<<blocks, kEwThreads, 0, s>>>(gd, a, w, ga, gw, gb, N, H, W);
+  REFID_CUDA_CHECK(launch_k(k_dw_bwd, dim3(blocks), dim3(kEwThreads), 0, s, gd, a, w, ga, gw, gb, N, H, W));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int launch_se_fwd(const float* pool_part, int parts, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
                   cudaStream_t st) {
-  k_se_fwd<<<N, 64, 0, st>>>(pool_part, parts, inv_hw, p, s, save_mean, save_z);
+  REFID_CUDA_CHECK(launch_k(k_se_fwd, dim3(N), dim3(64), 0, st, pool_part, parts, inv_hw, p, s, save_mean, save_z));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const float* save_z, float inv_hw, SeParams p,
                   float* gpool, int N, cudaStream_t st) {
-  k_se_bwd<<<N, 64, 0, st>>>(gs, s, save_mean, save_z, inv_hw, p, gpool);
+  REFID_CUDA_CHECK(launch_k(k_se_bwd, dim3(N), dim3(64), 0, st, gs, s, save_mean, save_z, inv_hw, p, gpool));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -692,7 +722,7 @@ int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const floa
                     cudaStream_t st) {
   unsigned blocks = blocks_for((long)N * hw * 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_gate_fwd<<<blocks, kEwThreads, 0, st>>>(gi, ge, s, cs, N, hw);
+  REFID_CUDA_CHECK(launch_k(k_gate_fwd, dim3(blocks), dim3(kEwThreads), 0, st, gi, ge, s, cs, N, hw));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -700,7 +730,7 @@ int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const floa
 int launch_gate_bwd_reduce(const __nv_bfloat16* gcs, const __nv_bfloat16* gi, const __nv_bfloat16* ge, float* gs, int N, long hw,
                            cudaStream_t st) {
   dim3 grid(blocks_for(hw, kGatePix), N);
-  k_gate_bwd_reduce<<<grid, kEwThreads, 0, st>>>(gcs, gi, ge, gs, hw);
+  REFID_CUDA_CHECK(launch_k(k_gate_bwd_reduce, dim3(grid), dim3(kEwThreads), 0, st, gcs, gi, ge, gs, hw));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -709,7 +739,7 @@ int launch_gate_bwd_apply(const __nv_bfloat16* gcs, const float* s, const float*
                           __nv_bfloat16* gz_de, int N, long hw, cudaStream_t st) {
   unsigned blocks = blocks_for((long)N * hw * 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k_gate_bwd_apply<<<blocks, kEwThreads, 0, st>>>(gcs, s, gpool, d_e, gi_f32, gz_de, N, hw);
+  REFID_CUDA_CHECK(launch_k(k_gate_bwd_apply, dim3(blocks), dim3(kEwThreads), 0, st, gcs, s, gpool, d_e, gi_f32, gz_de, N, hw));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -718,7 +748,7 @@ int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_d
   unsigned bx = blocks_for(max_elems, kEwThreads * 4);
   if (bx > 1024u) bx = 1024u;
   dim3 grid(bx, ndesc);
-  k_pack<<<grid, kEwThreads, 0, st>>>(flat, wpack, descs_dev);
+  REFID_CUDA_CHECK(launch_k(k_pack, dim3(grid), dim3(kEwThreads), 0, st, flat, wpack, descs_dev));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

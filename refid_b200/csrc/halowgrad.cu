@@ -128,11 +128,13 @@ __global__ void __launch_bounds__(kHWThreads, 1) halowgrad_kernel(const __grid_c
     tmem_alloc(tmem_slot, Cfg::COLS);
     tmem_relinquish();
   }
+  pdl_wait();  // set-up above overlaps the tail of the kernel before
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  pdl_launch_dependents();  // after the TMEM allocation (see haloconv.cu)
 
   if (t_end > t_begin) {
     if (warp == 0) {
@@ -383,7 +385,7 @@ int launch_hw_inst(HaloWgradParams& p, cudaStream_t stream) {
   if (stages > kHWMaxStages) stages = kHWMaxStages;
   p.num_stages = stages;
   const size_t smem = (size_t)stages * Cfg::STAGE + (2 * kHWMaxStages + 1) * sizeof(uint64_t) + 16 + 1024;
-  halowgrad_kernel<MODE><<<p.jobs * p.chunks, kHWThreads, smem, stream>>>(p);
+  REFID_CUDA_CHECK(launch_k(halowgrad_kernel<MODE>, dim3(p.jobs * p.chunks), dim3(kHWThreads), smem, stream, p));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

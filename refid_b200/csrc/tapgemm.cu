@@ -146,10 +146,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();  // set-up above overlaps the tail of the kernel before
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // after the TMEM allocation (see haloconv.cu)
 
   const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
   const int total_iters = total_slabs * p.num_taps;
@@ -249,7 +251,7 @@ int launch_inst(TapGemmParams& p, int n_blocks, cudaStream_t stream) {
   }
   const int tiles = p.tiles_x * p.tiles_y * ((p.N + p.TN - 1) / p.TN);
   dim3 grid(tiles, n_blocks);
-  tapgemm_kernel<BN, BK><<<grid, kThreads, smem, stream>>>(p);
+  REFID_CUDA_CHECK(launch_k(tapgemm_kernel<BN, BK>, dim3(grid), dim3(kThreads), smem, stream, p));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -46,10 +46,12 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
     tmem_alloc(tmem_slot, ncols);
     tmem_relinquish();
   }
+  pdl_wait();  // set-up above overlaps the tail of the kernel before
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // after the TMEM allocation (see haloconv.cu)
 
   if (my_tiles > 0 && my_mt > 0) {
     if (warp == 0) {
@@ -176,7 +178,7 @@ int launch_wgrad(WgradParams& p, int pixel_chunks, cudaStream_t stream) {
   if (pixel_chunks < 1) pixel_chunks = 1;
   const int mt_groups = (p.num_mtiles + p.mt_per_cta - 1) / p.mt_per_cta;
   dim3 grid(pixel_chunks, mt_groups, p.CQ / p.BNq);
-  wgrad_kernel<<<grid, kWThreads, smem, stream>>>(p);
+  REFID_CUDA_CHECK(launch_k(wgrad_kernel, dim3(grid), dim3(kWThreads), smem, stream, p));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
