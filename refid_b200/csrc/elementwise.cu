@@ -247,64 +247,95 @@ __global__ void __launch_bounds__(kEwThreads) k_ln_bwd(const __nv_bfloat16* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// depthwise 3x3 (C = 64): block = 32 pixels x 8 channel groups
+// depthwise 3x3 (C = 64), forward and backward.  A block stages the halo patch of an 8 x 32 pixel tile (10 x 34 pixels x
+// 128 B, zero-filled outside the image) in shared memory with cp.async and every thread walks one (column, 8-channel group)
+// down the tile's rows, reading its nine neighbours from shared memory: the nine-fold neighbourhood re-reads cost shared-
+// memory bandwidth instead of L2 round trips (the per-pixel version was latency-bound at 5-9x its HBM time).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
+constexpr int kDwPW = kDwTW + 2, kDwPH = kDwTH + 2;
+constexpr int kDwPatchBytes = kDwPH * kDwPW * 128;  // 43520
+
+__device__ __forceinline__ void dw_stage_patch(uint8_t* patch, const __nv_bfloat16* __restrict__ src, int n, int y0, int x0, int H,
+                                               int W) {
+  const uint32_t base = smem_u32(patch);
+  for (int i = threadIdx.x; i < kDwPH * kDwPW * 8; i += kEwThreads) {
+    const int px = i >> 3, chunk = i & 7;
+    const int y = y0 - 1 + px / kDwPW, x = x0 - 1 + px % kDwPW;
+    const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+    const __nv_bfloat16* g = src + (((size_t)n * H + (ok ? y : 0)) * W + (ok ? x : 0)) * 64 + chunk * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + (uint32_t)i * 16u), "l"(g), "r"(ok ? 16 : 0) : "memory");
+  }
+}
+__device__ __forceinline__ void dw_stage_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+__device__ __forceinline__ void lds8(const uint8_t* p, float* f) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
+  f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
+}
+
+// grid = (tiles per image, N): a block never straddles two samples, so the pooled sums are written as per-block partials
+// [N][dw_pool_parts(H, W)][64] and reduced in a fixed order by k_se_fwd (bit-reproducible forward pass)
+__global__ void __launch_bounds__(kEwThreads, 2) k_dw_fwd(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ d,
                                                        __nv_bfloat16* __restrict__ g, float* pool, int N, int H, int W) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float sw[64 * 9 + 64];
+  __shared__ __align__(16) uint8_t patch[kDwPatchBytes];
   __shared__ float spool[8][64];
-  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < 64) sw[64 * 9 + threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const long hw = (long)H * W;
-  // blockIdx.y = sample, blockIdx.x = 32-pixel chunk of that sample: a block never straddles two samples, so the pooled
-  // sums can be written as per-block partials and reduced in a fixed order (bit-reproducible forward pass)
-  const long pin = (long)blockIdx.x * 32 + pl;
-  const bool inside = pin < hw;
-  const long pix = (long)blockIdx.y * hw + pin;
-  float gv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (inside) {
-    const int n = (int)blockIdx.y;
-    const int y = (int)(pin / W), x = (int)(pin % W);
+  const int tiles_x = (W + kDwTW - 1) / kDwTW;
+  const int n = blockIdx.y, y0 = (blockIdx.x / tiles_x) * kDwTH, x0 = (blockIdx.x % tiles_x) * kDwTW;
+  dw_stage_patch(patch, a, n, y0, x0, H, W);
+  const int grp = threadIdx.x & 7, col = threadIdx.x >> 3;
+  float wr[8][9], br[8];  // this thread's 8 channels: weights and bias in registers
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    br[k] = bias[grp * 8 + k];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[k][t] = w[(grp * 8 + k) * 9 + t];
+  }
+  dw_stage_wait();
+  const int x = x0 + col;
+  float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+  for (int r = 0; r < kDwTH; ++r) {
+    const int y = y0 + r;
+    if (y >= H || x >= W) break;  // (x is loop-invariant: a column outside the image does nothing)
     float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = sw[64 * 9 + grp * 8 + k];
-    // (measured: issuing the nine neighbour loads unconditionally up front, as k_dw_bwd does, is SLOWER here -- 51 vs 43 us --
-    // this kernel is short, one pixel per thread, and the extra registers cost more occupancy than the batching wins)
+    for (int k = 0; k < 8; ++k) acc[k] = br[k];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= H) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= W) continue;
         float v[8];
-        load8(a + (((size_t)n * H + yy) * W + xx) * 64 + grp * 8, v);
+        lds8(patch + ((r + ky) * kDwPW + col + kx) * 128 + grp * 16, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k] * sw[(grp * 8 + k) * 9 + ky * 3 + kx];
+        for (int k = 0; k < 8; ++k) acc[k] += v[k] * wr[k][ky * 3 + kx];
       }
     }
-    float dg[8];  // the "pre-activation" buffer holds gelu'(z): the backward multiplies (ACT_MULT)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) gelu_both_f(acc[k], &gv[k], &dg[k]);
-    store8(d + (size_t)pix * 64 + grp * 8, dg);
-    store8(g + (size_t)pix * 64 + grp * 8, gv);
-  }
-  if (pool) {  // pool = per-block partial sums [N][gridDim.x][64]
+    float gv[8], dg[8];  // the "pre-activation" buffer holds gelu'(z): the backward multiplies (ACT_MULT)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 8);
-      gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], 16);
+      gelu_both_f(acc[k], &gv[k], &dg[k]);
+      psum[k] += gv[k];
+    }
+    const size_t off = (((size_t)n * H + y) * W + x) * 64 + grp * 8;
+    store8(d + off, dg);
+    store8(g + off, gv);
+  }
+  if (pool) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      psum[k] += __shfl_xor_sync(0xffffffffu, psum[k], 8);
+      psum[k] += __shfl_xor_sync(0xffffffffu, psum[k], 16);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane < 8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) spool[warp][lane * 8 + k] = gv[k];
+      for (int k = 0; k < 8; ++k) spool[warp][lane * 8 + k] = psum[k];
     }
     __syncthreads();
     if (threadIdx.x < 64) {
@@ -316,20 +347,24 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_fwd(const __nv_bfloat16* __re
   }
 }
 
-constexpr int kDwBwdPix = 256;  // pixels per block in the backward kernel (8 per thread)
+// Backward: ga[p] = sum_t gd[p - off_t] w[t];  gw[c][t] = sum_p a[p + off_t] gd[p];  gb[c] = sum_p gd[p].
+// Persistent blocks, one per SM, patches double-buffered (the next tile is staged while this one is computed): the weight-
+// gradient partials stay in registers over all of a block's tiles, so every output address receives one atomic per block.
+constexpr int kDwBwdSmem = 4 * kDwPatchBytes;
 
-__global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __restrict__ gd, const __nv_bfloat16* __restrict__ a,
-                                                       const float* __restrict__ w, __nv_bfloat16* __restrict__ ga, float* gw,
-                                                       float* gb, int N, int H, int W) {
+__global__ void __launch_bounds__(kEwThreads, 1) k_dw_bwd(const __nv_bfloat16* __restrict__ gd, const __nv_bfloat16* __restrict__ a,
+                                                          const float* __restrict__ w, __nv_bfloat16* __restrict__ ga, float* gw,
+                                                          float* gb, int N, int H, int W) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float sw[64 * 9];
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  __shared__ __align__(16) float sw[9 * 64];  // [tap][channel]
   __shared__ float sred[64 * 10];
-  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[(i % 9) * 64 + i / 9] = w[i];
   for (int i = threadIdx.x; i < 64 * 10; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
-  const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const long hw = (long)H * W, npix = (long)N * hw;
+  const int grp = threadIdx.x & 7, col = threadIdx.x >> 3;
+  const int tiles_x = (W + kDwTW - 1) / kDwTW, tiles_y = (H + kDwTH - 1) / kDwTH;
+  const int total = N * tiles_y * tiles_x;
   float aw[8][9];
   float ab[8];
 #pragma unroll
@@ -338,57 +373,53 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __re
 #pragma unroll
     for (int t = 0; t < 9; ++t) aw[k][t] = 0.f;
   }
-  // persistent blocks: the weight-gradient partials stay in registers over the block's whole pixel range, so every output
-  // address receives one atomic per BLOCK (<= #SMs) instead of one per 256 pixels (512 contended atomics per address)
-  for (long j = 0;; ++j) {
-    const long pix = ((long)blockIdx.x + j / (kDwBwdPix / 32) * gridDim.x) * kDwBwdPix + (j % (kDwBwdPix / 32)) * 32 + pl;
-    if (((long)blockIdx.x + j / (kDwBwdPix / 32) * gridDim.x) * kDwBwdPix >= npix) break;
-    if (pix >= npix) continue;
-    const int n = (int)(pix / hw);
-    const int y = (int)((pix % hw) / W), x = (int)(pix % W);
-    // All 18 neighbour chunks are fetched unconditionally (clamped address, zero weight outside the image) and BEFORE any
-    // use, so the loads are in flight together; with a branch around every load they were issued one latency at a time.
-    uint4 ra[9], rg[9];
-    float ma[9], mg[9];
+  auto stage = [&](int tile, int buf) {
+    const int n = tile / (tiles_y * tiles_x), y0 = ((tile / tiles_x) % tiles_y) * kDwTH, x0 = (tile % tiles_x) * kDwTW;
+    dw_stage_patch(dw_smem + (size_t)(2 * buf) * kDwPatchBytes, a, n, y0, x0, H, W);
+    dw_stage_patch(dw_smem + (size_t)(2 * buf + 1) * kDwPatchBytes, gd, n, y0, x0, H, W);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < total) stage(blockIdx.x, 0);
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, buf ^= 1) {
+    const int n = tile / (tiles_y * tiles_x), y0 = ((tile / tiles_x) % tiles_y) * kDwTH, x0 = (tile % tiles_x) * kDwTW;
+    const bool more = tile + (int)gridDim.x < total;
+    __syncthreads();  // the readers of the other buffer (previous tile) are done; sw / sred are initialised
+    if (more) stage(tile + gridDim.x, buf ^ 1);
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const uint8_t* pa = dw_smem + (size_t)(2 * buf) * kDwPatchBytes;
+    const uint8_t* pg = pa + kDwPatchBytes;
+    const int x = x0 + col;
+#pragma unroll 1
+    for (int r = 0; r < kDwTH; ++r) {
+      const int y = y0 + r;
+      float gc[8];
+      lds8(pg + ((r + 1) * kDwPW + col + 1) * 128 + grp * 16, gc);  // gd[p] (zero outside the image)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+      for (int k = 0; k < 8; ++k) ab[k] += gc[k];
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int t = ky * 3 + kx;
-        const int yy = y + ky - 1, xx = x + kx - 1;      // weight gradient: a[p + off] * gd[p]
-        const int y2 = y - (ky - 1), x2 = x - (kx - 1);  // data gradient:   gd[p - off] * w[tap]
-        ma[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? 1.f : 0.f;
-        mg[t] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? 1.f : 0.f;
-        const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
-        const int y2c = min(max(y2, 0), H - 1), x2c = min(max(x2, 0), W - 1);
-        ra[t] = *reinterpret_cast<const uint4*>(a + (((size_t)n * H + yc) * W + xc) * 64 + grp * 8);
-        rg[t] = *reinterpret_cast<const uint4*>(gd + (((size_t)n * H + y2c) * W + x2c) * 64 + grp * 8);
+      for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int t = ky * 3 + kx;
+          float v[8];
+          lds8(pa + ((r + ky) * kDwPW + col + kx) * 128 + grp * 16, v);  // a[p + off_t]
+#pragma unroll
+          for (int k = 0; k < 8; ++k) aw[k][t] += v[k] * gc[k];
+          lds8(pg + ((r + 2 - ky) * kDwPW + col + 2 - kx) * 128 + grp * 16, v);  // gd[p - off_t]
+          const float4 w0 = *reinterpret_cast<const float4*>(sw + t * 64 + grp * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sw + t * 64 + grp * 8 + 4);
+          acc[0] += v[0] * w0.x; acc[1] += v[1] * w0.y; acc[2] += v[2] * w0.z; acc[3] += v[3] * w0.w;
+          acc[4] += v[4] * w1.x; acc[5] += v[5] * w1.y; acc[6] += v[6] * w1.z; acc[7] += v[7] * w1.w;
+        }
       }
+      if (y < H && x < W) store8(ga + (((size_t)n * H + y) * W + x) * 64 + grp * 8, acc);
     }
-    float gc[8];
-    {
-      const uint4 c = rg[4];  // centre tap = gd[p]
-      gc[0] = bf16_lo(c.x); gc[1] = bf16_hi(c.x); gc[2] = bf16_lo(c.y); gc[3] = bf16_hi(c.y);
-      gc[4] = bf16_lo(c.z); gc[5] = bf16_hi(c.z); gc[6] = bf16_lo(c.w); gc[7] = bf16_hi(c.w);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) ab[k] += gc[k];
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      float v[8];
-      v[0] = bf16_lo(ra[t].x); v[1] = bf16_hi(ra[t].x); v[2] = bf16_lo(ra[t].y); v[3] = bf16_hi(ra[t].y);
-      v[4] = bf16_lo(ra[t].z); v[5] = bf16_hi(ra[t].z); v[6] = bf16_lo(ra[t].w); v[7] = bf16_hi(ra[t].w);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) aw[k][t] += ma[t] * v[k] * gc[k];
-      v[0] = bf16_lo(rg[t].x); v[1] = bf16_hi(rg[t].x); v[2] = bf16_lo(rg[t].y); v[3] = bf16_hi(rg[t].y);
-      v[4] = bf16_lo(rg[t].z); v[5] = bf16_hi(rg[t].z); v[6] = bf16_lo(rg[t].w); v[7] = bf16_hi(rg[t].w);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += mg[t] * v[k] * sw[(grp * 8 + k) * 9 + t];
-    }
-    store8(ga + (size_t)pix * 64 + grp * 8, acc);
   }
-  // reduce the 32 pixel lanes that share a channel group: lanes grp, grp+8, grp+16, grp+24 of each warp, then 8 warps
+  // reduce the 32 columns that share a channel group: lanes grp, grp+8, grp+16, grp+24 of each warp, then the 8 warps
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
 #pragma unroll
@@ -403,6 +434,7 @@ __global__ void __launch_bounds__(kEwThreads) k_dw_bwd(const __nv_bfloat16* __re
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     ab[k] = v;
   }
+  __syncthreads();
   if ((threadIdx.x & 31) < 8) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -696,10 +728,14 @@ int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __n
 
 int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* w, __nv_bfloat16* ga, float* gw, float* gb,
                   int N, int H, int W, cudaStream_t s) {
-  const long npix = (long)N * H * W;
-  unsigned blocks = blocks_for(npix, kDwBwdPix);
-  if (blocks > 148u) blocks = 148u;
-  REFID_CUDA_CHECK(launch_k(k_dw_bwd, dim3(blocks), dim3(kEwThreads), 0, s, gd, a, w, ga, gw, gb, N, H, W));
+  static bool attr_set = false;
+  if (!attr_set) {
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(k_dw_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwBwdSmem));
+    attr_set = true;
+  }
+  long blocks = (long)N * dw_pool_parts(H, W);
+  if (blocks > 148) blocks = 148;
+  REFID_CUDA_CHECK(launch_k(k_dw_bwd, dim3((unsigned)blocks), dim3(kEwThreads), (size_t)kDwBwdSmem, s, gd, a, w, ga, gw, gb, N, H, W));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

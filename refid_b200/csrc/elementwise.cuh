@@ -41,7 +41,8 @@ int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bf
 
 // Depthwise 3x3 (pad 1) over C = 64: z = dw(a) + bias, g = GELU(z), d = GELU'(z) (saved for the backward); pool[n][c] += sum_pix g.
 // pool (optional): per-block partial sums [N][dw_pool_parts(H, W)][64] fp32, reduced in fixed order by launch_se_fwd.
-inline int dw_pool_parts(int H, int W) { return (int)(((long)H * W + 31) / 32); }
+constexpr int kDwTH = 8, kDwTW = 32;  // depthwise-conv pixel tile
+inline int dw_pool_parts(int H, int W) { return ((H + kDwTH - 1) / kDwTH) * ((W + kDwTW - 1) / kDwTW); }
 int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
                   int N, int H, int W, cudaStream_t s);
 // ga = dw^T(gd); gw[c][tap] += sum a[p+tap] gd[p]; gb[c] += sum gd[p].
