@@ -88,6 +88,9 @@ int refid_num_launches(refid_handle h, int* fwd, int* bwd);
 /* Device pointer + shape of a named intermediate activation (NHWC bf16, `pitch` channels per pixel). */
 int refid_debug_tensor(refid_handle h, const char* name, void** ptr, int* N, int* H, int* W, int* C, int* pitch);
 int refid_abort_flag(unsigned int* out); /* non-zero: a bounded mbarrier wait timed out inside a kernel */
+/* Programmatic dependent launch (each kernel's set-up overlaps the tail of the kernel before it) on / off for all
+ * launches issued afterwards; default on unless the environment has REFID_PDL=0.  Returns the previous setting. */
+int refid_set_pdl(int enable);
 
 /* Single-kernel entry points (unit tests, ncu captures). */
 int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* in1, int C1, int N, int H, int W,

@@ -32,6 +32,11 @@ def ptr(t):
     return c_void_p(0 if t is None else t.data_ptr())
 
 
+def set_pdl(enable):
+    """Programmatic dependent launch on/off for subsequent launches; returns the previous setting."""
+    return bool(lib().refid_set_pdl(1 if enable else 0))
+
+
 def abort_flag():
     v = ctypes.c_uint(0)
     check(lib().refid_abort_flag(ctypes.byref(v)), "refid_abort_flag")

@@ -16,13 +16,18 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static int g_pdl = -1;
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_pdl < 0) {
     const char* e = getenv("REFID_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
   }
-  return v != 0;
+  return g_pdl != 0;
+}
+int set_pdl(int enable) {
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl = enable ? 1 : 0;
+  return prev;
 }
 
 

@@ -1789,6 +1789,8 @@ int refid_profile_csv(refid_handle h, int with_backward, const char* path, void*
   return 0;
 }
 
+int refid_set_pdl(int enable) { return refid::set_pdl(enable); }
+
 int refid_num_launches(refid_handle h, int* fwd, int* bwd) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (fwd) *fwd = (int)e->fwd.size();

@@ -117,6 +117,36 @@ def test_multi_tile_shape_and_eval_mode():
             assert abs(p_ref - p_mine) < 0.01, (b, t, p_ref, p_mine)
 
 
+def test_dependent_launch_does_not_change_results():
+    """Programmatic dependent launch only moves kernel set-up ahead of the predecessor's completion: the forward output is
+    bit-identical with it on and off (ragged 72x104 frames, so depthwise-conv and halo tiles straddle the image edge),
+    and the parameter gradients agree to float-atomic reordering."""
+    from oracle import refid_oracle as O
+    from refid_b200 import _lib
+    B, T, H, W, ic, ec = 2, 2, 72, 104, 6, 2
+    P = paramgen.make_params(O.param_shapes(ic, ec), seed=3)
+    x, ev, gt = paramgen.make_inputs(B, T, H, W, ic, ec, x5d=True)
+    outs, grads = [], []
+    prev = _lib.set_pdl(True)
+    try:
+        for enable in (True, False):
+            _lib.set_pdl(enable)
+            net = _net(ic, ec, P)
+            out = net(x=x.cuda(), event=ev.cuda())
+            (out.float() - gt.cuda()).abs().mean().backward()
+            torch.cuda.synchronize()
+            outs.append(out.detach().clone())
+            grads.append({k: v.grad.detach().clone() for k, v in net.named_parameters() if v.grad is not None})
+    finally:
+        _lib.set_pdl(prev)
+    _no_abort()
+    assert torch.equal(outs[0], outs[1])
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 0
+    for k in grads[0]:
+        a, b = grads[0][k], grads[1][k]
+        assert (a - b).abs().max().item() <= 1e-3 * max(1.0, b.abs().max().item()), k
+
+
 def test_no_cpu_path():
     from refid_b200.arch import FinalBidirectionAttenfusion
     net = FinalBidirectionAttenfusion(img_chn=6, ev_chn=2, num_encoders=3, base_num_channels=32, num_block=1)

@@ -9,4 +9,5 @@ timeout 600 python tools/layer_profile.py 8 23 256 256 layersT23_$tag > gpurun_o
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$tag.csv python tools/profile_step.py 2 4 256 256 > gpurun_out/ncu_list_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"haloconv_kernel<\(int\)(64|128|256), \(int\)[12], \(int\)9, \(int\)64" -s 10 -c 7 -f -o gpurun_out/prof_haloconv_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_halo_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:halowgrad -c 3 -f -o gpurun_out/prof_halowgrad_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_wgrad_$tag.log 2>&1
+for u in umma_rate umma_pattern umma_smem_contention; do timeout 120 ./tools/ubench/$u > gpurun_out/${u}_$tag.txt 2>&1; done
 ls -la gpurun_out/*.ncu-rep

@@ -70,6 +70,6 @@ int main() {
   run<N, NM, 1>(d, "halo patch, no shifts, SBO 1280"); \
   run<N, NM, 2>(d, "dense tile, no shifts, SBO 1024"); \
   run<N, NM, 3>(d, "kernel pattern, one weight tile for all taps");
-  ALL(32, 2) ALL(64, 1) ALL(64, 2) ALL(128, 2)
+  ALL(32, 2) ALL(64, 1) ALL(64, 2)
   return 0;
 }

@@ -18,13 +18,21 @@ __global__ void __launch_bounds__(128, 1) k_rate(int M, int N, int iters, int a_
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_bf16(M, N, 0, 0);
     const uint32_t a0 = smem_u32(smem), b0 = a0 + 96 * 1024;
-    long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      // 4 K-steps per "stage"; rotate over distinct smem regions so reads are real
-      const uint32_t aa = a0 + (uint32_t)((it & 3) * a_stride), bb = b0 + (uint32_t)((it & 3) * b_stride);
+    // descriptors are built BEFORE the timed loop: the tcgen05 queue is ~1 MMA deep, so descriptor arithmetic between MMAs
+    // would be measured as MMA time (an earlier version of this loop did that and reported 62.5 cycles for every N <= 96)
+    uint64_t da[4], db[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        umma_bf16(tm + (uint32_t)((it & 1) * N), make_smem_desc(aa + a_off + k * 32, 16, a_sbo, 2), make_smem_desc(bb + k * 32, 16, 1024, 2), idesc, 1);
+    for (int u = 0; u < 4; ++u) {
+      da[u] = make_smem_desc(a0 + (uint32_t)(u * a_stride) + a_off, 16, a_sbo, 2);
+      db[u] = make_smem_desc(b0 + (uint32_t)(u * b_stride), 16, 1024, 2);
+    }
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it += 4) {
+      // 4 K-steps per "stage"; rotate over distinct smem regions so reads are real
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tm + (uint32_t)((u & 1) * N), da[u] + (uint64_t)(k * 2), db[u] + (uint64_t)(k * 2), idesc, 1);
       }
     }
     umma_commit(&bar);
