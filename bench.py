@@ -193,11 +193,14 @@ def main():
     x, ev, gt = hx.to(dev), hev.to(dev), hgt.to(dev)
     h2d = sum(t.numel() * t.element_size() for t in (hx, hev, hgt))
 
+    from refid_b200.losses import CharbonnierLoss
+    cri_pix = CharbonnierLoss(loss_weight=1.0, reduction="mean")  # train.pixel_opt of the GoPro option files
+
     def step(xd, evd, gtd):
         for p in net.parameters():
             p.grad = None
         out = net(x=xd, event=evd)
-        loss = torch.sqrt((out - gtd) ** 2 + 1e-12).mean()  # CharbonnierLoss (basicsr/models/losses/losses.py:28-30)
+        loss = cri_pix(out, gtd)  # twoImage_event_recurrent_model.py:284; value + gradient in one CUDA pass (csrc/loss.cu)
         loss.backward()
         return loss
 
@@ -261,7 +264,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": (nf + nb) * args.steps, "clocks": clk.summary(),
+            "gpu_launches": (nf + nb + 3) * args.steps,  # plan launches + loss, loss finish, upstream-gradient scale
+            "clocks": clk.summary(),
             "samples_per_s": value / T}
     if rank == 0:
         pk = peaks()

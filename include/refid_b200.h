@@ -92,6 +92,16 @@ int refid_abort_flag(unsigned int* out); /* non-zero: a bounded mbarrier wait ti
  * launches issued afterwards; default on unless the environment has REFID_PDL=0.  Returns the previous setting. */
 int refid_set_pdl(int enable);
 
+/* Charbonnier loss, value and gradient in one pass (replaces CharbonnierLoss.forward + its autograd
+ * backward, basicsr/models/losses/losses.py:28-30,143-173): loss = loss_weight * (mean | sum) sqrt((pred-target)^2 + eps),
+ * grad (nullable) = d loss / d pred.  fp32, n elements, 16-byte aligned; `scratch` = refid_charbonnier_scratch_bytes()
+ * bytes of device memory; `loss` = one device float.  Asynchronous on `stream`, bit-reproducible. */
+int refid_charbonnier_scratch_bytes(void);
+int refid_charbonnier(const float* pred, const float* target, float* grad, void* scratch, float* loss, long n, float eps,
+                      float loss_weight, int reduction_mean, void* stream);
+/* x[0..n) *= *scalar (one device float; e.g. the upstream gradient of the loss); no memory traffic when it is exactly 1. */
+int refid_scale_by_device_scalar(float* x, const float* scalar, long n, void* stream);
+
 /* Single-kernel entry points (unit tests, ncu captures). */
 int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* in1, int C1, int N, int H, int W,
                     const void* w, long w_rows, int w_cols, int wrows_per_tap, int w_row0, int Cout, const float* bias,

@@ -9,3 +9,4 @@
 #include "elementwise.cu"
 #include "engine.cu"
 #include "api_test.cu"
+#include "loss.cu"

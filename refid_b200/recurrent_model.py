@@ -13,11 +13,10 @@ from copy import deepcopy
 
 import torch
 
+from . import losses as loss_module
 from .plugin import define_network
 
 
-def charbonnier(pred, target, eps=1e-12):
-    return torch.sqrt((pred - target) ** 2 + eps).mean()
 
 
 class TwoImageEventRecurrentRestorationModel:
@@ -33,7 +32,8 @@ class TwoImageEventRecurrentRestorationModel:
             pix = train_opt.get("pixel_opt") or {"type": "CharbonnierLoss"}
             if pix.get("type", "CharbonnierLoss") != "CharbonnierLoss":
                 raise NotImplementedError("only CharbonnierLoss is used by the shipped option files")
-            self.loss_weight = float(pix.get("loss_weight", 1.0))
+            pix = dict(pix)
+            self.cri_pix = getattr(loss_module, pix.pop("type", "CharbonnierLoss"))(**pix).to(self.device)  # :52-58
             og = train_opt.get("optim_g", {"type": "AdamW", "lr": 2e-4, "weight_decay": 1e-4, "betas": [0.9, 0.99]})
             og = dict(og)
             optim_type = og.pop("type")
@@ -55,7 +55,7 @@ class TwoImageEventRecurrentRestorationModel:
     def optimize_parameters(self, current_iter=0):
         self.optimizer_g.zero_grad()
         pred = self.net_g(x=self.lq, event=self.voxel)
-        l_pix = self.loss_weight * charbonnier(pred, self.gt)
+        l_pix = self.cri_pix(pred, self.gt)  # :284
         l_total = l_pix + 0 * sum(p.sum() for p in self.net_g.parameters())
         l_total.backward()
         if self.opt["train"].get("use_grad_clip", True):
