@@ -102,6 +102,19 @@ int refid_charbonnier(const float* pred, const float* target, float* grad, void*
 /* x[0..n) *= *scalar (one device float; e.g. the upstream gradient of the loss); no memory traffic when it is exactly 1. */
 int refid_scale_by_device_scalar(float* x, const float* scalar, long n, void* stream);
 
+/* Global-norm gradient clip + Adam / AdamW step over all parameter tensors as two multi-tensor passes (SURVEY.md 8f rank
+ * 2; replaces `torch.nn.utils.clip_grad_norm_(net_g.parameters(), 0.01)` + `optimizer_g.step()`,
+ * basicsr/models/twoImage_event_recurrent_model.py:304-307, optimizer set-up :67-95).  `numel[i]` elements per tensor, fixed
+ * at create; per step the caller passes host arrays of fp32 device pointers (a NULL gradient skips that parameter, as torch
+ * does).  max_norm <= 0: no clipping.  `steps[i]` = 1-based step count of tensor i (bias correction).  decoupled = 1: AdamW, 0: Adam with
+ * L2 weight decay.  norm_out (optional, device, 2 floats) receives {total gradient norm, clip coefficient}.
+ * Gradients are NOT rescaled in memory (the reference's clipped .grad tensors are never read again).  Asynchronous. */
+int refid_optim_create(int ntensors, const long* numel, void** handle);
+int refid_optim_destroy(void* handle);
+int refid_optim_step(void* handle, float* const* params, const float* const* grads, float* const* exp_avg,
+                     float* const* exp_avg_sq, float max_norm, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, const long* steps, int decoupled, float* norm_out, void* stream);
+
 /* Single-kernel entry points (unit tests, ncu captures). */
 int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* in1, int C1, int N, int H, int W,
                     const void* w, long w_rows, int w_cols, int wrows_per_tap, int w_row0, int Cout, const float* bias,

@@ -10,3 +10,4 @@
 #include "engine.cu"
 #include "api_test.cu"
 #include "loss.cu"
+#include "optim.cu"

@@ -3,7 +3,8 @@
   * `optimize_parameters`  -- basicsr/models/twoImage_event_recurrent_model.py:273-310: zero_grad, `net_g(x=lq,
     event=voxel)`, Charbonnier loss (losses.py:28-30, eps 1e-12, mean), the `+ 0 * sum(p.sum())` term that gives the
     never-used parameters a zero gradient (:301), backward, `clip_grad_norm_(..., 0.01)` unless `use_grad_clip: false`
-    (:304-306), optimizer step (AdamW / Adam from `train.optim_g`, :67-95);
+    (:304-306), optimizer step (AdamW / Adam from `train.optim_g`, :67-95) -- clip and step are one fused multi-tensor
+    update (`refid_b200.optim`);
   * `test` -- :312-330: eval + no_grad, `val.max_minibatch` chunking, outputs concatenated on dim 0.
 
 Data loading, validation bookkeeping, logging, checkpoints and schedulers stay with the reference (out of scope,
@@ -14,6 +15,7 @@ from copy import deepcopy
 import torch
 
 from . import losses as loss_module
+from . import optim
 from .plugin import define_network
 
 
@@ -39,9 +41,9 @@ class TwoImageEventRecurrentRestorationModel:
             optim_type = og.pop("type")
             params = [p for p in self.net_g.parameters() if p.requires_grad]
             if optim_type == "AdamW":
-                self.optimizer_g = torch.optim.AdamW(params, **og)
+                self.optimizer_g = optim.ClipAdamW(params, **og)
             elif optim_type == "Adam":
-                self.optimizer_g = torch.optim.Adam(params, **og)
+                self.optimizer_g = optim.ClipAdam(params, **og)
             else:
                 raise NotImplementedError(f"optimizer {optim_type} is not supperted yet.")
         self.log_dict = {}
@@ -59,7 +61,7 @@ class TwoImageEventRecurrentRestorationModel:
         l_total = l_pix + 0 * sum(p.sum() for p in self.net_g.parameters())
         l_total.backward()
         if self.opt["train"].get("use_grad_clip", True):
-            torch.nn.utils.clip_grad_norm_(self.net_g.parameters(), 0.01)
+            self.optimizer_g.clip_grad_norm_(0.01)  # :304-306, fused into the step below
         self.optimizer_g.step()
         self.log_dict = {"l_pix": l_pix.detach()}
         return l_pix.detach()

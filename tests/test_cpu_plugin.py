@@ -34,7 +34,8 @@ def test_wrapper_needs_cuda_and_keeps_reference_defaults():
     from refid_b200 import plugin, recurrent_model
     opt = plugin.load_options(os.path.join(ROOT, "options/train/GoPro_blurry_11p1_b200.yml"))
     m = recurrent_model.TwoImageEventRecurrentRestorationModel(opt, device="cpu")
-    assert isinstance(m.optimizer_g, torch.optim.AdamW)
+    from refid_b200 import optim
+    assert isinstance(m.optimizer_g, optim.ClipAdamW) and isinstance(m.optimizer_g, torch.optim.Optimizer)
     g = m.optimizer_g.param_groups[0]
     assert g["lr"] == 2e-4 and g["weight_decay"] == 1e-4 and tuple(g["betas"]) == (0.9, 0.99)
     m.feed_data({"lq": torch.rand(1, 26, 32, 32), "voxel": torch.rand(1, 2, 2, 32, 32), "gt": torch.rand(1, 2, 3, 32, 32)})
