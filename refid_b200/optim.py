@@ -28,6 +28,8 @@ class _ClipAdamBase(torch.optim.Optimizer):
         self._handle = None
         self._key = None
         self._norm = None
+        self._tables = None
+        self._steps = None
 
     def clip_grad_norm_(self, max_norm):
         """Global 2-norm clip of all gradients to `max_norm`, fused into the next step()."""
@@ -36,6 +38,20 @@ class _ClipAdamBase(torch.optim.Optimizer):
     def last_grad_norm(self):
         """(total gradient norm, clip coefficient) of the last step, as a device tensor of two floats."""
         return self._norm
+
+    def _sync_steps(self):
+        if getattr(self, "_tables", None) is not None:
+            groups = [g for g in self.param_groups if len(g["params"]) > 0]
+            for p, k in zip(groups[0]["params"], self._steps):
+                self.state[p]["step"].fill_(float(k))
+
+    def state_dict(self):
+        self._sync_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = None  # the moment tensors and step counts were replaced
 
     def __del__(self):
         try:
@@ -55,43 +71,54 @@ class _ClipAdamBase(torch.optim.Optimizer):
             raise NotImplementedError("one non-empty parameter group (the reference's option files produce exactly one)")
         g = groups[0]
         params = [p for p in g["params"]]
-        for p in params:
-            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                raise RuntimeError("ClipAdamW needs contiguous fp32 CUDA parameters (no CPU path)")
         L = _lib.lib()
+        n = len(params)
         key = tuple((p.data_ptr(), p.numel()) for p in params)
         if key != self._key:
+            for p in params:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("ClipAdamW needs contiguous fp32 CUDA parameters (no CPU path)")
             if self._handle is not None:
                 _lib.check(L.refid_optim_destroy(self._handle), "refid_optim_destroy")
-            numel = (ctypes.c_long * len(params))(*[p.numel() for p in params])
+            numel = (ctypes.c_long * n)(*[p.numel() for p in params])
             h = ctypes.c_void_p()
             with torch.cuda.device(params[0].device):
-                _lib.check(L.refid_optim_create(len(params), numel, ctypes.byref(h)), "refid_optim_create")
+                _lib.check(L.refid_optim_create(n, numel, ctypes.byref(h)), "refid_optim_create")
             self._handle, self._key = h, key
             self._norm = torch.zeros(2, dtype=torch.float32, device=params[0].device)
-        any_grad = False
-        for p in params:
-            st = self.state[p]
-            if len(st) == 0:
-                st["step"] = torch.tensor(0.0)
-                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            if p.grad is not None:
-                st["step"] += 1
-                any_grad = True
-        if not any_grad:
+            self._tables = None
+        if self._tables is None or any(len(self.state[p]) == 0 for p in params):
+            # torch's state layout; the host keeps the step counts as ints and writes them into the `step` tensors only
+            # when the state is exported (183 scalar tensor updates per step would cost more host time than the kernels)
+            for p in params:
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            VP = ctypes.c_void_p * n
+            self._steps = [int(self.state[p]["step"].item()) for p in params]
+            self._tables = (VP, VP(*[p.data_ptr() for p in params]), VP(*[self.state[p]["exp_avg"].data_ptr() for p in params]),
+                            VP(*[self.state[p]["exp_avg_sq"].data_ptr() for p in params]))
+            L.refid_optim_step.argtypes = [ctypes.c_void_p, VP, VP, VP, VP, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                           ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_long * n, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p]
+        VP, a_p, a_m, a_v = self._tables
+        keep, ptrs, steps = [], [], self._steps
+        for i, p in enumerate(params):
+            gr = p.grad
+            if gr is None:
+                ptrs.append(None)
+                continue
+            if gr.dtype != torch.float32 or not gr.is_contiguous():
+                gr = gr.detach().float().contiguous()
+                keep.append(gr)
+            ptrs.append(gr.data_ptr())
+            steps[i] += 1
+        if all(q is None for q in ptrs):
             return loss
-        n = len(params)
-        a_steps = (ctypes.c_long * n)(*[int(self.state[p]["step"].item()) for p in params])
-        VP = ctypes.c_void_p * n
-        keep = [None if p.grad is None else p.grad.detach().float().contiguous() for p in params]
-        a_p = VP(*[p.data_ptr() for p in params])
-        a_g = VP(*[None if t is None else t.data_ptr() for t in keep])
-        a_m = VP(*[self.state[p]["exp_avg"].data_ptr() for p in params])
-        a_v = VP(*[self.state[p]["exp_avg_sq"].data_ptr() for p in params])
-        L.refid_optim_step.argtypes = [ctypes.c_void_p, VP, VP, VP, VP, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_long * n, ctypes.c_int,
-                                       ctypes.c_void_p, ctypes.c_void_p]
+        a_g = VP(*ptrs)
+        a_steps = (ctypes.c_long * n)(*steps)
         stream = ctypes.c_void_p(torch.cuda.current_stream(params[0].device).cuda_stream)
         with torch.cuda.device(params[0].device):
             _lib.check(L.refid_optim_step(self._handle, a_p, a_g, a_m, a_v, self._max_norm, g["lr"], g["betas"][0], g["betas"][1],
