@@ -115,6 +115,16 @@ int refid_optim_step(void* handle, float* const* params, const float* const* gra
                      float* const* exp_avg_sq, float max_norm, float lr, float beta1, float beta2, float eps,
                      float weight_decay, const long* steps, int decoupled, float* norm_out, void* stream);
 
+/* tensor2img quantisation + PSNR sums on the GPU (replaces `tensor2img` on result and gt followed by
+ * `calculate_psnr`, basicsr/utils/img_util.py:59-121, basicsr/metrics/psnr_ssim.py:9-61, per validation frame).  pred / gt:
+ * `frames` x (C,H,W) fp32 on the device.  Every value is clamped to [0,1], x255, rounded half to even.  With gt != NULL:
+ * ssd[f] = exact integer sum of squared uint8 differences inside the crop border, max_pred[f] = largest quantised pred
+ * value there (calculate_psnr's `max_value` rule); PSNR = 20 log10(255 / sqrt(ssd / count)) is formed by the caller in
+ * double.  img_pred / img_gt (nullable): the uint8 images, (H,W,C) per frame, channels reversed (RGB -> BGR) if asked. */
+int refid_quant_psnr(const float* pred, const float* gt, int frames, int C, int H, int W, int crop_border,
+                     int reverse_channels, unsigned long long* ssd, unsigned int* max_pred, unsigned char* img_pred,
+                     unsigned char* img_gt, void* stream);
+
 /* Single-kernel entry points (unit tests, ncu captures). */
 int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* in1, int C1, int N, int H, int W,
                     const void* w, long w_rows, int w_cols, int wrows_per_tap, int w_row0, int Cout, const float* bias,

@@ -11,3 +11,4 @@
 #include "api_test.cu"
 #include "loss.cu"
 #include "optim.cu"
+#include "metrics.cu"
