@@ -125,6 +125,14 @@ int refid_quant_psnr(const float* pred, const float* gt, int frames, int C, int 
                      int reverse_channels, unsigned long long* ssd, unsigned int* max_pred, unsigned char* img_pred,
                      unsigned char* img_gt, void* stream);
 
+/* Event -> voxel-grid rasterisation (replaces `events_to_voxel_grid`, basicsr/data/event_util.py:6-66).
+ * events: n rows of float32 [timestamp, x, y, polarity] on the device (the reference's array layout), 16-byte aligned;
+ * voxel: (num_bins,height,width) fp32, or (height,width,num_bins) with hwc != 0; scratch: num_bins*height*width*8 bytes.
+ * Time span = first and last row's stamps, polarity 0 counts as -1, bilinear weights in double, accumulated exactly in
+ * fixed point (bit-reproducible); events outside the grid are dropped.  Asynchronous on `stream`. */
+int refid_events_to_voxel(const float* events, long n, int num_bins, int width, int height, int hwc, void* scratch,
+                          float* voxel, void* stream);
+
 /* Single-kernel entry points (unit tests, ncu captures). */
 int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* in1, int C1, int N, int H, int W,
                     const void* w, long w_rows, int w_cols, int wrows_per_tap, int w_row0, int Cout, const float* bias,

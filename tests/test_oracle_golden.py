@@ -47,3 +47,24 @@ def test_psnr_restatement():
     b = (a + 0.01).clamp(0, 1)
     p = O.psnr_uint8(O.tensor2img_uint8(a), O.tensor2img_uint8(b))
     assert 35 < p < 45
+
+
+EVENT_CASES = ["events_2bin_64x48", "events_5bin_40x40", "events_same_stamp", "events_dense_pixel"]
+
+
+@pytest.mark.parametrize("case", EVENT_CASES)
+def test_event_oracle_matches_reference_golden(case):
+    """oracle/event_oracle.py against the voxel grids the unmodified reference function produced
+    (tests/golden/make_event_golden.py): bit-exact -- same float32 / float64 arithmetic in the same order."""
+    import os
+    import numpy as np
+    from oracle import event_oracle as E
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", case + ".npz"))
+    n, bins, w, h, seed, srt = [int(v) for v in z["meta"]]
+    ev = E.synthetic_events(n, w, h, seed, bool(srt))
+    if case == "events_same_stamp":
+        ev[:, 0] = 7.0
+    out = E.events_to_voxel_grid(ev, bins, w, h, "CHW")
+    assert out.dtype == np.float32 and out.shape == z["voxel"].shape
+    assert np.array_equal(out, z["voxel"])
+    assert np.array_equal(E.events_to_voxel_grid(ev, bins, w, h, "HWC"), z["voxel"].transpose(1, 2, 0))
