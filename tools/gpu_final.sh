@@ -10,4 +10,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"haloconv_kernel<\(int\)(64|128|256), \(int\)[12], \(int\)9, \(int\)64" -s 10 -c 7 -f -o gpurun_out/prof_haloconv_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_halo_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:halowgrad -c 3 -f -o gpurun_out/prof_halowgrad_$tag python tools/profile_step.py 8 2 256 256 > gpurun_out/ncu_wgrad_$tag.log 2>&1
 for u in umma_rate umma_pattern umma_smem_contention; do timeout 120 ./tools/ubench/$u > gpurun_out/${u}_$tag.txt 2>&1; done
+timeout 300 python tools/host_launch_probe.py > gpurun_out/host_launch_$tag.txt 2>&1; tail -n 1 gpurun_out/host_launch_$tag.txt
+timeout 300 python tools/callers_bench.py > gpurun_out/callers_bench_$tag.txt 2>&1
 ls -la gpurun_out/*.ncu-rep
