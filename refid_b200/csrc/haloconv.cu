@@ -367,8 +367,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           if (elect_one()) {
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) {
-              constexpr int dummy = 0;
-              (void)dummy;
               const uint32_t tap_off = (uint32_t)(((TAPS == 9 ? tap / 3 : 0)) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * PXB;
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
