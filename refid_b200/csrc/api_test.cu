@@ -76,11 +76,5 @@ int refid_test_wgrad(int kind, const void* p0, int C0, const void* p1, int C1, i
   return run_wgrad(l, static_cast<cudaStream_t>(stream));
 }
 
-#ifdef REFID_HALO_TIMING
-// diagnostic build only: per-CTA cycle counters of the halo-conv MMA warp (total, acc wait, A wait, B wait, issue, items)
-int refid_debug_halo_timing(long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, g_halo_t, sizeof(long long) * 148 * 8) == cudaSuccess ? 0 : 1;
-}
-#endif
 
 }  // extern "C"

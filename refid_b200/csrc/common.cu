@@ -31,12 +31,58 @@ int set_pdl(int enable) {
 }
 
 
+// ---- abort flags: one device copy per translation unit + one pinned host word (see common.cuh) ----
+namespace {
+struct AbortReg {
+  const void* flag;
+  const void* host_ptr;
+};
+AbortReg g_abort_regs[32];
+int g_abort_nregs = 0;
+volatile unsigned int* g_abort_host_word = nullptr;  // pinned + mapped
+bool g_abort_published = false;
+}  // namespace
+
+void register_abort_flag(const void* flag_symbol, const void* host_ptr_symbol) {
+  if (g_abort_nregs < 32) g_abort_regs[g_abort_nregs++] = AbortReg{flag_symbol, host_ptr_symbol};
+}
+
+// Hands every translation unit the device address of the pinned host word (once per process, first GPU call).
+static int publish_abort_word() {
+  if (g_abort_published) return 0;
+  unsigned int* h = nullptr;
+  REFID_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+  *h = 0;
+  unsigned int* d = nullptr;
+  REFID_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0));
+  for (int i = 0; i < g_abort_nregs; ++i)
+    REFID_CUDA_CHECK(cudaMemcpyToSymbol(g_abort_regs[i].host_ptr, &d, sizeof(d)));
+  g_abort_host_word = h;
+  g_abort_published = true;
+  return 0;
+}
+
+unsigned int abort_pending() {
+  if (!g_abort_published && publish_abort_word()) return 0xFFFFFFFFu;
+  return *g_abort_host_word;
+}
+
 int read_and_clear_abort_flag(cudaStream_t stream, unsigned int* out) {
-  unsigned int v = 0, z = 0;
+  unsigned int first = 0, z = 0;
+  if (publish_abort_word()) return 1;
   REFID_CUDA_CHECK(cudaStreamSynchronize(stream));
-  REFID_CUDA_CHECK(cudaMemcpyFromSymbol(&v, g_abort_flag, sizeof(v)));
-  if (v) REFID_CUDA_CHECK(cudaMemcpyToSymbol(g_abort_flag, &z, sizeof(z)));
-  *out = v;
+  REFID_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < g_abort_nregs; ++i) {
+    unsigned int v = 0;
+    REFID_CUDA_CHECK(cudaMemcpyFromSymbol(&v, g_abort_regs[i].flag, sizeof(v)));
+    if (v) {
+      REFID_CUDA_CHECK(cudaMemcpyToSymbol(g_abort_regs[i].flag, &z, sizeof(z)));
+      if (!first) first = v;
+    }
+  }
+  if (!first) first = *g_abort_host_word;
+  *g_abort_host_word = 0;
+  *out = first;
   return 0;
 }
 

@@ -32,9 +32,31 @@ const char* get_error();
     }                                            \
   } while (0)
 
-// Device-side abort flag: a bounded mbarrier wait that times out records a code here instead of hanging.
-__device__ unsigned int g_abort_flag = 0;  // unity build: defined once here
+// Device-side abort flag: a bounded mbarrier wait that times out records a code instead of hanging.  Every translation
+// unit carries its own copy of the device flag (no relocatable device code) and registers it with common.cu; the timeout
+// path also writes the code into ONE pinned, device-mapped host word, which `abort_pending()` reads without any
+// synchronisation: refid_forward / refid_backward (and the Python callers at their sync points) refuse to continue once
+// it is set, so a protocol bug can never silently turn later pipelines into unsynchronised ones.
+static __device__ unsigned int g_abort_flag = 0;
+static __device__ unsigned int* g_abort_host = nullptr;  // device view of the pinned host word (null until registered)
+void register_abort_flag(const void* flag_symbol, const void* host_ptr_symbol);
+unsigned int abort_pending();  // sticky host-side view (no sync); 0 = healthy
 int read_and_clear_abort_flag(cudaStream_t stream, unsigned int* out);
+namespace {
+struct AbortFlagRegistration {
+  AbortFlagRegistration() { register_abort_flag((const void*)&g_abort_flag, (const void*)&g_abort_host); }
+};
+static AbortFlagRegistration g_abort_registration;
+}  // namespace
+#define REFID_REQUIRE_HEALTHY(what)                                                                              \
+  do {                                                                                                           \
+    const unsigned int _a = ::refid::abort_pending();                                                            \
+    if (_a) {                                                                                                    \
+      ::refid::set_error("%s refused: an earlier kernel hit its bounded mbarrier wait (code 0x%x); results since " \
+                         "then are invalid -- call refid_abort_flag() to read and clear", what, _a);             \
+      return 1;                                                                                                  \
+    }                                                                                                            \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // tensor maps
@@ -118,7 +140,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22) || *((volatile unsigned int*)&g_abort_flag) != 0) {
-      atomicCAS(&g_abort_flag, 0u, code);
+      if (atomicCAS(&g_abort_flag, 0u, code) == 0u && g_abort_host) {
+        *((volatile unsigned int*)g_abort_host) = code;  // pinned host word: visible to the host without a sync
+        __threadfence_system();
+      }
       return;
     }
   }

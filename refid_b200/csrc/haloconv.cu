@@ -658,3 +658,10 @@ int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream
 }
 
 }  // namespace refid
+
+#ifdef REFID_HALO_TIMING
+// diagnostic build only: per-CTA cycle counters of the halo-conv MMA warp (total, acc wait, A wait, B wait, issue, items)
+extern "C" int refid_debug_halo_timing(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, refid::g_halo_t, sizeof(long long) * 148 * 8) == cudaSuccess ? 0 : 1;
+}
+#endif
