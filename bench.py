@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""Benchmark of the REFID hot path (forward + Charbonnier loss + backward of FinalBidirectionAttenfusion).
+"""Benchmark of the REFID hot path (FinalBidirectionAttenfusion forward / backward on the sm_100a engine).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload gopro_11p1|gopro_7skip|tiny]
+    python bench.py --gpus N --steps K --warmup W [--impl reference|reference-cuda] [--workload NAME] [--mode train|infer]
 
-One "step" = one training iteration's network work on one batch of synthetic GoPro-shaped input:
-forward, Charbonnier loss, backward to every parameter gradient, and (N > 1) the NCCL all-reduce of the flat gradient.
-Metric: output frames / second = B*T*N / step time.  Default workload = BASELINE.json configs[1]
-(GoPro blurry VFI 11+1: x (8,26,256,256), event (8,23,2,256,256), bf16 compute, per GPU).
+Training mode (default): one "step" = one training iteration's network work on one batch of synthetic input (SURVEY.md
+8d): forward, Charbonnier loss, backward to every parameter gradient, and (N > 1) the NCCL all-reduce of the flat
+gradient.  Inference mode: one step = one no_grad forward.  Metric: output frames / second = B*T*N / step time.
+Default workload = BASELINE.json configs[1] (GoPro blurry VFI 11+1: x (8,26,256,256), event (8,23,2,256,256), bf16).
 
-`--impl reference` times the reference's algorithm on the host CPU cores (the fp32 oracle port in oracle/, all
-threads) on a bounded sample of the same workload.  Prints ONE JSON line on rank 0.
+Reference arms (rank 0 only):
+  --impl reference       the UNMODIFIED reference module (oracle/_ref staged files, else /root/reference; the oracle port if
+                         neither is there) on the host cores, all threads, fp32, on ONE sample of the same workload at
+                         full T and resolution (no extrapolation: the reference's per-frame CPU cost does not depend on B);
+  --impl reference-cuda  the same unmodified module on the GPU through PyTorch/cuDNN: fp32 with TF32 convolutions and
+                         cudnn.benchmark (the reference's train.py setting) and bf16 autocast + channels_last (the stronger
+                         baseline), at the largest batch <= the workload's that fits.
+Prints ONE JSON line on rank 0.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -24,12 +32,15 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (B per GPU, T, H, W, img_chn, ev_chn)
-    "gopro_11p1": (8, 23, 256, 256, 26, 2),   # BASELINE.json configs[1]
-    "gopro_7skip": (8, 7, 256, 256, 6, 2),    # configs[2] per GPU
-    "highrev_11p3": (2, 25, 512, 512, 26, 2),  # configs[3] per GPU
+    "gopro_11p1": (8, 23, 256, 256, 26, 2),     # BASELINE.json configs[1]  (the metric's configuration)
+    "gopro_7skip": (8, 7, 256, 256, 6, 2),      # configs[2] per GPU
+    "highrev_11p3": (2, 25, 512, 512, 26, 2),   # configs[3] per GPU
+    "fullres_720p": (1, 15, 720, 1280, 6, 2),   # configs[4]: inference only
+    "gopro_11p1_b1": (1, 23, 256, 256, 26, 2),  # the reference's own training batch (1 per GPU): launch-bound regime
     "tiny": (1, 3, 64, 64, 26, 2),
 }
 METRIC = "frames/sec fwd+bwd 256x256 GoPro 11+1"
+NET_KW = dict(num_encoders=3, base_num_channels=32, num_block=1, num_residual_blocks=2)
 
 
 def algorithmic_gflop_fwd(T, H, W, img_chn, ev_chn):
@@ -63,6 +74,16 @@ def init_params(net, seed=0):
         for n, p in net.named_parameters():
             if n.endswith(".beta") or n.endswith(".gamma"):
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
+
+
+def bench_state_dict(ic, ec):
+    """The benchmark's parameters as a CPU state_dict (both arms and the parity check use exactly these)."""
+    import torch
+    from refid_b200.arch import FinalBidirectionAttenfusion
+    torch.manual_seed(0)
+    net = FinalBidirectionAttenfusion(img_chn=ic, ev_chn=ec, **NET_KW)
+    init_params(net)
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
 
 
 class ClockSampler:
@@ -113,30 +134,116 @@ def peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
-def cpu_reference_run(B, T, H, W, ic, ec, steps, warmup, sample_T=None, sample_hw=None):
-    """The fp32 oracle port (oracle/refid_oracle.py) fwd + Charbonnier + bwd on the host cores."""
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arms (the only places bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_module(ic, ec, state_dict):
+    """(module, kind): the unmodified reference network with the benchmark's parameters, or the oracle port."""
+    from oracle import ref_loader
+    if ref_loader.available():
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = ref_loader.build(ic, ec)
+        net.load_state_dict(state_dict, strict=True)
+        return net, "reference", ref_loader.source()
     import torch
     from oracle import refid_oracle as O
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import paramgen  # deterministic O(1)-scale parameters shared with the parity tests
+
+    class Port(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.P = torch.nn.ParameterDict({k.replace(".", "/"): torch.nn.Parameter(v.clone()) for k, v in state_dict.items()})
+
+        def forward(self, x, event):
+            return O.forward({k.replace("/", "."): v for k, v in self.P.items()}, x, event)
+
+    return Port(), "port", "oracle/refid_oracle.py (reference files not staged)"
+
+
+def charbonnier(out, gt):
+    import torch
+    return torch.sqrt((out.float() - gt) ** 2 + 1e-12).mean()  # basicsr/models/losses/losses.py:28-30
+
+
+def cpu_reference_run(T, H, W, ic, ec, steps, warmup, train=True, state_dict=None, inputs=None):
+    """The reference on the host cores: ONE sample of the workload at full T and resolution; fwd + Charbonnier + bwd (or a
+    no_grad forward).  Returns (frames/s, s/step, cores, kind, sample text, output of the last step)."""
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Ts = sample_T or T
-    Hs, Ws = sample_hw or (H, W)
-    P = paramgen.make_params(O.param_shapes(ic, ec), seed=0)
-    x, ev, gt = make_inputs(1, Ts, Hs, Ws, ic, ec, seed=1234)
-    times = []
+    sd = state_dict if state_dict is not None else bench_state_dict(ic, ec)
+    net, kind, src = reference_module(ic, ec, sd)
+    x, ev, gt = inputs if inputs is not None else make_inputs(1, T, H, W, ic, ec, seed=1234)
+    times, out = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.loss_and_grads(P, x, ev, gt)
+        if train:
+            for p in net.parameters():
+                p.grad = None
+            out = net(x=x, event=ev)
+            charbonnier(out, gt).backward()
+        else:
+            with torch.no_grad():
+                out = net(x=x, event=ev)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    # per-frame CPU cost is linear in pixels and in T (same convs per pixel per step)
-    fps = Ts / sec * (Hs * Ws) / (H * W)
-    sample = f"B=1, T={Ts}, {Hs}x{Ws} crop of the workload, fwd+Charbonnier+bwd, fp32, {cores} threads, {steps} timed steps; " \
-             f"frames/s scaled by pixel count to {H}x{W}"
-    return fps, sec, cores, sample
+    what = "fwd+Charbonnier+bwd" if train else "no_grad forward"
+    sample = (f"one sample (B=1) of the workload at full size: T={T}, {H}x{W}, {what}, fp32, {cores} threads, {steps} timed "
+              f"step(s) after {warmup} warm-up; {src}; frames/s = T / step time (per-frame CPU cost is independent of B)")
+    return T / sec, sec, cores, kind, sample, out.detach()
+
+
+def cuda_reference_run(B, T, H, W, ic, ec, steps, warmup, train=True, state_dict=None):
+    """The unmodified reference module on the GPU through PyTorch/cuDNN.  Two settings: fp32 with TF32 convs and
+    cudnn.benchmark (the reference's train.py:139), and bf16 autocast + channels_last.  Batch = the largest power-of-two
+    fraction of B that fits (the fp32 path keeps ~0.75 GB of activations per step and sample at 256^2)."""
+    import torch
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    sd = state_dict if state_dict is not None else bench_state_dict(ic, ec)
+    res = {}
+    for mode in ("fp32_tf32", "bf16_autocast_channels_last"):
+        b = B
+        while b >= 1:
+            try:
+                net, kind, src = reference_module(ic, ec, sd)
+                net = net.cuda()
+                if mode != "fp32_tf32":
+                    net = net.to(memory_format=torch.channels_last)
+                x, ev, gt = make_inputs(b, T, H, W, ic, ec, seed=1234, device="cuda")
+
+                def step():
+                    with torch.autocast("cuda", torch.bfloat16, enabled=(mode != "fp32_tf32")):
+                        if train:
+                            for p in net.parameters():
+                                p.grad = None
+                            out = net(x=x, event=ev)
+                        else:
+                            with torch.no_grad():
+                                out = net(x=x, event=ev)
+                    if train:
+                        charbonnier(out, gt).backward()
+                for _ in range(max(warmup, 2)):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                res[mode] = {"batch": b, "ms_per_step": ms, "frames_per_s": b * T / (ms * 1e-3), "kind": kind,
+                             "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+                break
+            except torch.cuda.OutOfMemoryError:
+                b //= 2
+            finally:
+                net = x = ev = gt = None
+                torch.cuda.empty_cache()
+        if mode not in res:
+            res[mode] = {"error": "out of memory at batch 1"}
+    return res
 
 
 def main():
@@ -144,64 +251,95 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="gopro_11p1", choices=list(WORKLOADS))
+    ap.add_argument("--mode", default=None, choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
     args = ap.parse_args()
     B, T, H, W, ic, ec = WORKLOADS[args.workload]
+    mode = args.mode or ("infer" if args.workload == "fullres_720p" else "train")
+    train = mode == "train"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = METRIC if (args.workload == "gopro_11p1" and train) else \
+        f"frames/sec {'fwd+bwd' if train else 'forward (no_grad)'} {args.workload}"
+    step_text = ("forward + Charbonnier loss + backward to all parameter gradients (+ flat-gradient NCCL all-reduce if N>1)"
+                 if train else "no_grad forward (fp16 storage), output kept on the device")
     config = {"workload": f"{args.workload}: x ({B},{ic},{H},{W}) + event ({B},{T},{ec},{H},{W}) per GPU, T={T} output frames",
-              "batch_per_gpu": B, "T": T, "H": H, "W": W, "img_chn": ic, "ev_chn": ec,
-              "step": "forward + Charbonnier loss + backward to all parameter gradients (+ flat-gradient NCCL all-reduce if N>1)",
-              "l2": "per-step working set (tens of GB of saved activations) far exceeds the 126 MB L2; no explicit flush"}
+              "mode": mode, "batch_per_gpu": B, "T": T, "H": H, "W": W, "img_chn": ic, "ev_chn": ec, "step": step_text,
+              "l2": "per-step working set (GBs of activations) far exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample: a 128x128 crop with T=4 event slices keeps one step at a few seconds of CPU time
-        fps, sec, cores, sample = cpu_reference_run(B, T, H, W, ic, ec, max(1, args.steps), max(1, min(args.warmup, 1)),
-                                                    sample_T=min(T, 4), sample_hw=(min(H, 128), min(W, 128)))
-        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        fps, sec, cores, kind, sample, _ = cpu_reference_run(T, H, W, ic, ec, max(1, args.steps), max(0, min(args.warmup, 1)),
+                                                            train=train)
+        line = {"impl": "reference", "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     import torch
     import torch.distributed as dist
-    from refid_b200.arch import FinalBidirectionAttenfusion
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+
+    if args.impl == "reference-cuda":
+        if rank != 0:
+            return
+        res = cuda_reference_run(B, T, H, W, ic, ec, max(1, args.steps), args.warmup, train=train)
+        ok = {k: v for k, v in res.items() if "frames_per_s" in v}
+        best = max(ok, key=lambda k: ok[k]["frames_per_s"]) if ok else None
+        line = {"impl": "reference-cuda", "metric": metric, "value": ok[best]["frames_per_s"] if best else None,
+                "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ok[best]["ms_per_step"] if best else None, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": best, "data": "synthetic", "config": config, "modes": res,
+                "note": "unmodified reference module on the same GPU through PyTorch/cuDNN; value = the faster setting"}
+        print(json.dumps(line))
+        return
+
+    from refid_b200 import _lib
+    from refid_b200.arch import FinalBidirectionAttenfusion
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(0)
-    net = FinalBidirectionAttenfusion(img_chn=ic, ev_chn=ec, num_encoders=3, base_num_channels=32, num_block=1,
-                                      num_residual_blocks=2)
-    init_params(net)
+    sd = bench_state_dict(ic, ec)
+    net = FinalBidirectionAttenfusion(img_chn=ic, ev_chn=ec, **NET_KW)
+    net.load_state_dict(sd, strict=True)
     net = net.to(dev)
-    if world > 1:
+    if not train:
+        net.eval()
+    if world > 1 and train:
         net.grad_sync_group = dist.group.WORLD  # flat-gradient all-reduce (mean) inside the backward
     hx, hev, hgt = make_inputs(B, T, H, W, ic, ec, seed=1234 + rank, pin=True)
     x, ev, gt = hx.to(dev), hev.to(dev), hgt.to(dev)
-    h2d = sum(t.numel() * t.element_size() for t in (hx, hev, hgt))
+    h2d = sum(t.numel() * t.element_size() for t in ((hx, hev, hgt) if train else (hx, hev)))
 
     from refid_b200.losses import CharbonnierLoss
     cri_pix = CharbonnierLoss(loss_weight=1.0, reduction="mean")  # train.pixel_opt of the GoPro option files
+    last = {}
 
     def step(xd, evd, gtd):
+        if not train:
+            with torch.no_grad():
+                out = net(x=xd, event=evd)
+            last["out"] = out
+            return out
         for p in net.parameters():
             p.grad = None
         out = net(x=xd, event=evd)
         loss = cri_pix(out, gtd)  # twoImage_event_recurrent_model.py:284; value + gradient in one CUDA pass (csrc/loss.cu)
         loss.backward()
+        last["out"], last["loss"] = out, loss
         return loss
 
     def barrier():
@@ -224,19 +362,31 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step(x, ev, gt)
+    if args.no_graphs:
+        for s in net._states.values():
+            s["engine"].set_option("graphs", 0)
     with ClockSampler(local_rank) as clk:
         ms = timed(lambda: step(x, ev, gt), args.steps)
+    _lib.raise_if_aborted()
     frames = B * T * world * args.steps
     value = frames / (ms * 1e-3)
+    out0 = last["out"][0].detach().float().cpu()  # sample 0 of the last timed step, for the parity record below
+    if train:
+        loss_value = float(last["loss"].item())
+        if not (loss_value == loss_value and abs(loss_value) < 1e6):
+            raise SystemExit(f"bench: the training loss is not finite ({loss_value})")
+    if not bool(torch.isfinite(last["out"]).all()):
+        raise SystemExit("bench: the network output is not finite")
 
-    # end to end: every step copies its inputs from pinned host memory and reads the loss back to the host.  As in the
-    # reference's CUDAPrefetcher (basicsr/data/prefetch_dataloader.py) the copy of step i+1 runs on a side stream while
-    # step i computes; one copy is issued per step inside the timed region.
+    # end to end: every step copies its inputs from pinned host memory and reads the result (the loss; in inference mode
+    # the mean of the output) back to the host.  As in the reference's CUDAPrefetcher (basicsr/data/prefetch_dataloader.py)
+    # the copy of step i+1 runs on a side stream while step i computes; one copy is issued per step inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
+    hosts = (hx, hev, hgt) if train else (hx, hev)
 
     def h2d_async():
         with torch.cuda.stream(copy_stream):
-            t = (hx.to(dev, non_blocking=True), hev.to(dev, non_blocking=True), hgt.to(dev, non_blocking=True))
+            t = tuple(h.to(dev, non_blocking=True) for h in hosts)
             e = torch.cuda.Event()
             e.record(copy_stream)
         return t, e
@@ -244,37 +394,41 @@ def main():
     pending = [h2d_async()]
 
     def e2e_step():
-        (xd, evd, gtd), e = pending.pop()
+        t, e = pending.pop()
         cur = torch.cuda.current_stream()
         cur.wait_event(e)
         pending.append(h2d_async())
-        loss = step(xd, evd, gtd)
-        for t in (xd, evd, gtd):
-            t.record_stream(cur)
-        return loss.item()
+        r = step(t[0], t[1], t[2] if train else None)
+        for q in t:
+            q.record_stream(cur)
+        return r.item() if train else r.mean().item()
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = frames / (ms_e2e * 1e-3)
 
-    st = next(s for k, s in net._states.items() if k[4])
+    st = next(s for k, s in net._states.items() if bool(k[4]) == train)
     nf, nb = st["engine"].num_launches()
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    gstats = st["engine"].graph_stats()
+    line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": "bf16" if train else "fp16", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": (nf + nb + 3) * args.steps,  # plan launches + loss, loss finish, upstream-gradient scale
+            # plan launches (+ loss, loss finish, upstream-gradient scale in training); replayed from CUDA graphs
+            "gpu_launches": (nf + (nb + 3 if train else 0)) * args.steps,
+            "cuda_graphs": gstats,
             "clocks": clk.summary(),
-            "samples_per_s": value / T}
+            "samples_per_s": value / T,
+            "workspace_gib": st["engine"].workspace_bytes(B, T, H, W, train) / 2 ** 30}
     if rank == 0:
         pk = peaks()
-        gf = 3.0 * algorithmic_gflop_fwd(T, H, W, ic, ec) * B  # fwd + dgrad + wgrad, per GPU per step
+        gf = (3.0 if train else 1.0) * algorithmic_gflop_fwd(T, H, W, ic, ec) * B  # fwd (+ dgrad + wgrad), per GPU per step
         step_tflops = gf / (ms / args.steps)  # GFLOP / ms = TFLOP/s
         line["step_tflops_algorithmic"] = step_tflops
         line["step_frac_of_bf16_sustained"] = step_tflops / pk["bf16_sustained"]
         if not args.no_profile:
-            prof = st["engine"].profile(True)
+            prof = st["engine"].profile(train)
             torch.cuda.synchronize()
             # dominant kernel: haloconv_kernel on the stride-1 3x3 convs with >= 64 channels (forward + data-gradient)
             conv = {k: prof[k] for k in ("conv3x3_fwd", "conv3x3_dgrad")}
@@ -284,24 +438,46 @@ def main():
             tot = sum(v["ms"] for v in prof.values())
             ach = cfl / (cms * 1e-3) / 1e12
             traffic = None
-            tp = os.path.join(ROOT, "profiles", "r01_ncu_haloconv.json")
-            if os.path.exists(tp):  # dram bytes per launch from the committed `ncu --set full` capture of the same kernel
-                caps = [c for c in json.load(open(tp)) if "haloconv" in c.get("kernel", "")]
-                if caps:
-                    traffic = 1e6 * sum(c["dram_read_MB"] + c["dram_write_MB"] for c in caps) / len(caps)
+            for name in ("r02_ncu_haloconv.json", "r01_ncu_haloconv.json"):
+                tp = os.path.join(ROOT, "profiles", name)
+                if os.path.exists(tp):  # dram bytes per launch from the committed `ncu --set full` capture of the same kernel
+                    caps = [c for c in json.load(open(tp)) if "haloconv" in c.get("kernel", "")]
+                    if caps:
+                        traffic = 1e6 * sum(c["dram_read_MB"] + c["dram_write_MB"] for c in caps) / len(caps)
+                        traffic_src = name
+                        break
             line["roofline"] = {"bound": "tensor",
                                 "kernel": "haloconv_kernel (stride-1 3x3 implicit-GEMM conv, >= 64 channels, forward + data-gradient, tcgen05)",
                                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                                 "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                                "traffic": traffic, "traffic_note": "mean dram read+write bytes per captured launch (profiles/r01_ncu_haloconv.json)",
+                                "traffic": traffic,
+                                "traffic_note": f"mean dram read+write bytes per captured launch (profiles/{traffic_src})" if traffic else None,
                                 "launches_per_step": cn, "avg_launch_ms": cms / max(cn, 1),
                                 "share_of_step_device_time": cms / tot,
                                 "per_class": {k: {"ms": v["ms"], "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] else 0.0,
                                                   "launches": v["launches"]} for k, v in prof.items()}}
         if not args.no_cpu_baseline and world == 1:
-            fps, sec, cores, sample = cpu_reference_run(B, T, H, W, ic, ec, 2, 1, sample_T=min(T, 4),
-                                                        sample_hw=(min(H, 128), min(W, 128)))
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+            # the reference on the host cores on sample 0 of this very batch, with these very parameters: the timing is the
+            # cpu_baseline, its output is the parity record of the timed configuration (all T frames of sample 0)
+            fps, sec, cores, kind, sample, ref_out = cpu_reference_run(
+                T, H, W, ic, ec, 1, 0, train=train, state_dict=sd, inputs=(hx[0:1].clone(), hev[0:1].clone(), hgt[0:1].clone()))
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+            d = (out0 - ref_out[0]).abs()
+            line["parity"] = {"max_abs_err_vs_reference": d.max().item(), "rms_err": d.pow(2).mean().sqrt().item(),
+                              "frames": T, "sample": 0, "tolerance": 2e-2 if train else 2e-3,
+                              "storage": "bf16" if train else "fp16"}
+            if not d.max().item() < line["parity"]["tolerance"]:
+                raise SystemExit(f"bench: output of the timed configuration differs from the reference: {line['parity']}")
+        if not args.no_ref_cuda and world == 1 and train:
+            # context for the north-star's ">= 5x the reference PyTorch-CUDA path": free our workspace first
+            net.release_buffers()
+            del st
+            torch.cuda.empty_cache()
+            rc = cuda_reference_run(B, T, H, W, ic, ec, 2, 2, train=True, state_dict=sd)
+            line["reference_cuda"] = rc
+            best = max((v["frames_per_s"] for v in rc.values() if "frames_per_s" in v), default=None)
+            line["ref_cuda_frames_s"] = best
+            line["speedup_vs_reference_cuda"] = (value / best) if best else None
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

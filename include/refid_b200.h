@@ -58,7 +58,8 @@ int refid_param_entry_at(refid_handle h, int idx, refid_param_entry* out);
 long refid_flat_floats(refid_handle h);    /* length of the flat fp32 parameter / gradient vectors */
 size_t refid_wpack_bytes(refid_handle h);  /* persistent device buffer: fp32 master copy + bf16 UMMA-ready packs */
 
-/* Bytes of workspace (activations saved for backward, gradient pool) for one (B,T,H,W) problem. H, W % 8 == 0. */
+/* Bytes of workspace for one (B,T,H,W) problem; H, W % 8 == 0.  train != 0: every activation the backward needs for all
+ * T steps plus the gradient pool; train == 0: per-step buffers are recycled, O(1) in T apart from the hoisted event head. */
 int refid_workspace_bytes(refid_handle h, int B, int T, int H, int W, int train, size_t* out);
 
 /* Build the launch plan (TMA tensor maps are encoded here) for fixed buffers.  grad_flat may be NULL when train == 0. */
@@ -72,6 +73,18 @@ int refid_forward(refid_handle h, const float* x, const float* event, float* out
 /* grad_out: (B,T,out_chn,H,W) fp32.  Zeroes grad_flat, then accumulates d(loss)/d(flat) into it.
  * Must follow a refid_forward on the same plan (train != 0). */
 int refid_backward(refid_handle h, const float* grad_out, void* stream);
+
+/* Engine options (name, value):
+ *   "infer_fp16" (default 1; set before refid_plan): forward-only plans (train == 0) keep activations and packed weights
+ *       as fp16 instead of bf16 -- same bytes and tensor-core rate, 11 instead of 8 significant bits, which brings the
+ *       output within ~1e-3 max-abs / 2.5e-4 RMS of the fp32 reference (the PSNR-parity bar); training plans are bf16.
+ *   "graphs" (default 1): refid_forward / refid_backward replay their launch list as a CUDA graph once the same
+ *       (x, event, out) / grad_out pointers are seen a second time; 0 = plain launches.
+ * refid_graph_stats: {graphs captured, graph replays, eager runs, capture failures}.  refid_plan_storage: 1 = the current
+ * plan stores fp16, 0 = bf16. */
+int refid_set_option(refid_handle h, const char* name, long value);
+int refid_graph_stats(refid_handle h, long out[4]);
+int refid_plan_storage(refid_handle h);
 
 /* Roofline accounting: re-runs forward (+ backward) of the current plan on the tensors of the last call with a CUDA
  * event pair around every launch; sums device milliseconds, algorithmic FLOPs and launch counts per class:
@@ -87,7 +100,10 @@ int refid_profile_csv(refid_handle h, int with_backward, const char* path, void*
 int refid_num_launches(refid_handle h, int* fwd, int* bwd);
 /* Device pointer + shape of a named intermediate activation (NHWC bf16, `pitch` channels per pixel). */
 int refid_debug_tensor(refid_handle h, const char* name, void** ptr, int* N, int* H, int* W, int* C, int* pitch);
-int refid_abort_flag(unsigned int* out); /* non-zero: a bounded mbarrier wait timed out inside a kernel */
+int refid_abort_flag(unsigned int* out); /* non-zero: a bounded mbarrier wait timed out inside a kernel; synchronises, clears */
+/* Same condition without synchronising or clearing (a pinned host word the timing-out kernel writes): once non-zero,
+ * refid_forward / refid_backward refuse to run until refid_abort_flag() has been called. */
+unsigned int refid_abort_pending(void);
 /* Programmatic dependent launch (each kernel's set-up overlaps the tail of the kernel before it) on / off for all
  * launches issued afterwards; default on unless the environment has REFID_PDL=0.  Returns the previous setting. */
 int refid_set_pdl(int enable);

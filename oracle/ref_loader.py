@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference arch files from /root/reference (build container only).
+"""Import the UNMODIFIED reference arch files: from /root/reference in the build container, else from the byte-for-byte
+staged copies under oracle/_ref/ (oracle/make_ref.py; git-ignored, shipped to the GPU box like the built .so).
 
-TEST INFRASTRUCTURE.  Used by tests/golden/make_golden.py and by the optional container-only test that
-re-validates the oracle against the live reference.  /root/reference does not exist on the GPU box, so nothing
-that runs there may call this.
+TEST / BENCH INFRASTRUCTURE.  Used by tests/golden/make_golden.py, the live-reference validation of the oracle, and the
+reference arms of bench.py (`--impl reference` on the host cores, `--impl reference-cuda` on the GPU).  Never imported by
+refid_b200/.
 
 The reference package's own __init__ chain needs lmdb/timm/skimage and a missing h5_image_dataset.py
 (SURVEY.md section 0), so stub packages are pre-seeded in sys.modules and only the four arch files
@@ -14,11 +15,26 @@ import os
 import sys
 import types
 
-REF = os.environ.get("REFID_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick():
+    for cand in (os.environ.get("REFID_REFERENCE"), "/root/reference", _STAGED):
+        if cand and os.path.isfile(f"{cand}/basicsr/models/archs/XXNet_final_attenfusion_arch.py"):
+            return cand
+    return "/root/reference"
+
+
+REF = _pick()
 
 
 def available() -> bool:
     return os.path.isfile(f"{REF}/basicsr/models/archs/XXNet_final_attenfusion_arch.py")
+
+
+def source() -> str:
+    """Where the reference files are read from ('live' tree or the 'staged' byte-for-byte copies)."""
+    return "staged oracle/_ref" if os.path.abspath(REF) == os.path.abspath(_STAGED) else f"live {REF}"
 
 
 def load():

@@ -41,3 +41,13 @@ def abort_flag():
     v = ctypes.c_uint(0)
     check(lib().refid_abort_flag(ctypes.byref(v)), "refid_abort_flag")
     return v.value
+
+
+def raise_if_aborted():
+    """Sticky, sync-free health check (pinned host word written by a kernel whose bounded mbarrier wait timed out)."""
+    L = lib()
+    L.refid_abort_pending.restype = ctypes.c_uint
+    v = L.refid_abort_pending()
+    if v:
+        raise RuntimeError(f"refid_b200: a kernel hit its bounded mbarrier wait (code 0x{v:x}); results after it are "
+                           "invalid. refid_b200._lib.abort_flag() reads and clears the flag.")

@@ -91,9 +91,29 @@ def _evr_layer(cin, c, fuse, atten):  # SimpleRecurrentThenDownAttenfusionmodifi
 def sync_flat_grad(g, group):
     """In-place mean of the flat gradient over the data-parallel group (one all-reduce; NCCL on GPUs, gloo in tests)."""
     import torch.distributed as dist
-    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-    g.div_(dist.get_world_size(group))
+    if g.is_cuda:
+        dist.all_reduce(g, op=dist.ReduceOp.AVG, group=group)  # NCCL averages in the reduction itself
+    else:  # gloo has no AVG
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        g.div_(dist.get_world_size(group))
     return g
+
+
+def broadcast_parameters(module, group, src=0):
+    """Rank `src`'s parameters and buffers to every rank of `group` -- what DistributedDataParallel does at construction
+    (reference base_model.py:66-72).  The reference seeds rank r with `manual_seed + r` (train.py:56), so without this
+    the replicas would start from different weights and, applying the same averaged gradient, never meet."""
+    import torch.distributed as dist
+    ts = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    if not ts:
+        return
+    flat = torch.cat([t.reshape(-1).float() for t in ts])
+    dist.broadcast(flat, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    off = 0
+    with torch.no_grad():
+        for t in ts:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
 
 
 class _RefidFunction(torch.autograd.Function):
@@ -104,7 +124,9 @@ class _RefidFunction(torch.autograd.Function):
         train = bool(ctx.needs_input_grad[2])
         st = mod._state_for(B, T, H, W, train, x.device)
         eng = st["engine"]
-        eng.pack_weights(flat.detach().contiguous())
+        if flat is not None:  # None: the packed weights of this plan are current (forward-only call, parameters unchanged)
+            eng.pack_weights(flat.detach().contiguous())
+            st["packed_key"] = mod._pending_key
         out = torch.empty(B, T, mod.out_chn, H, W, device=x.device, dtype=torch.float32)
         eng.forward(x, event, out)
         st["generation"] += 1
@@ -132,8 +154,14 @@ class FinalBidirectionAttenfusion(nn.Module):
 
     def __init__(self, img_chn, ev_chn, out_chn=3, skip_type='sum', recurrent_block_type='convlstm', activation='sigmoid',
                  num_encoders=4, base_num_channels=32, num_residual_blocks=2, norm=None, use_recurrent_upsample_conv=True,
-                 num_block=3, use_first_dcn=False, use_reversed_voxel=False):
+                 num_block=3, use_first_dcn=False, use_reversed_voxel=False, infer_dtype='fp16'):
         super().__init__()
+        # `infer_dtype` is the one key this backend adds to `network_g` (default keeps every shipped option file valid):
+        # 16-bit storage type of forward-only (no_grad) calls -- 'fp16' (11 significant bits; output within ~1e-3 of the
+        # fp32 reference, PSNR within 0.01 dB) or 'bf16' (bit-identical to the training forward).  Training is bf16.
+        if infer_dtype not in ('fp16', 'bf16'):
+            raise ValueError("infer_dtype must be 'fp16' or 'bf16'")
+        self.infer_dtype = infer_dtype
         # Configurations no shipped option file uses are refused rather than silently diverging.
         for name, got, want in (("skip_type", skip_type, 'sum'), ("norm", norm, None), ("num_encoders", num_encoders, 3),
                                 ("num_block", num_block, 1), ("num_residual_blocks", num_residual_blocks, 2),
@@ -179,9 +207,24 @@ class FinalBidirectionAttenfusion(nn.Module):
             d.forward_trunk = _trunk(cin, cin // 2)
             self.decoders.append(d)
         self.pred = _conv_layer(b, out_chn, 3, 1)
-        self.grad_sync_group = None  # set to a torch.distributed group for the flat-gradient all-reduce (no DDP wrapper)
+        self._grad_sync_group = None
         self._engines = {}   # device -> Engine (parameter table)
         self._states = {}    # (B,T,H,W,train,device) -> planned engine + buffers
+
+    # ------------------------------------------------------------------------------------------
+    # data parallelism without the DDP wrapper
+    # ------------------------------------------------------------------------------------------
+    @property
+    def grad_sync_group(self):
+        """torch.distributed group for the flat-gradient all-reduce inside backward (None: no collective).  Assigning a
+        group also broadcasts rank 0's parameters to the group, as DDP's constructor does."""
+        return self._grad_sync_group
+
+    @grad_sync_group.setter
+    def grad_sync_group(self, group):
+        self._grad_sync_group = group
+        if group is not None:
+            broadcast_parameters(self, group)
 
     # ------------------------------------------------------------------------------------------
     # parameters -> the engine's flat vector
@@ -259,11 +302,12 @@ class FinalBidirectionAttenfusion(nn.Module):
         st = self._states.get(key)
         if st is None:
             eng = _engine.Engine(self.img_chn, self.ev_chn, self.out_chn, 32)
+            eng.set_option("infer_fp16", self.infer_dtype == 'fp16')
             ws = torch.empty(eng.workspace_bytes(B, T, H, W, train), dtype=torch.uint8, device=device)
             wpack = torch.empty(eng.wpack_bytes, dtype=torch.uint8, device=device)
             grad_flat = torch.zeros(eng.flat_floats, dtype=torch.float32, device=device) if train else None
             eng.plan(B, T, H, W, train, ws, wpack, grad_flat)
-            st = {"engine": eng, "grad_flat": grad_flat, "generation": 0}
+            st = {"engine": eng, "grad_flat": grad_flat, "generation": 0, "packed_key": None}
             self._states[key] = st
         return st
 
@@ -289,11 +333,23 @@ class FinalBidirectionAttenfusion(nn.Module):
                              f"ev_chn={self.ev_chn}")
         if H % 8 or W % 8:
             raise ValueError("H and W must be multiples of 8 (three stride-2 levels)")
-        flat = self._flat(self._table_engine())
+        params = list(self.parameters())
+        self._pending_key = tuple((p.data_ptr(), p._version) for p in params)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            flat = self._flat(self._table_engine())  # differentiable: autograd maps the flat gradient back through the folds
+        else:
+            # forward-only: the flat vector and the packed weights are rebuilt only when a parameter changed since this
+            # plan last packed them (every in-place update bumps the parameter's version counter; refid_b200.optim does too)
+            st = self._state_for(B, T, H, W, False, x.device)
+            flat = None
+            if st["packed_key"] != self._pending_key:
+                with torch.no_grad():
+                    flat = self._flat(self._table_engine())
         return _RefidFunction.apply(x.float().contiguous(), event.float().contiguous(), flat, self)
 
     def extra_repr(self):
-        return f"img_chn={self.img_chn}, ev_chn={self.ev_chn}, out_chn={self.out_chn}, backend=librefid_b200.so (sm_100a)"
+        return (f"img_chn={self.img_chn}, ev_chn={self.ev_chn}, out_chn={self.out_chn}, infer_dtype={self.infer_dtype}, "
+                f"backend=librefid_b200.so (sm_100a)")
 
 
 def flat_param_count(img_chn, ev_chn):

@@ -8,6 +8,7 @@ extern "C" {
 const char* refid_last_error(void) { return get_error(); }
 
 int refid_abort_flag(unsigned int* out) { return read_and_clear_abort_flag(0, out); }
+unsigned int refid_abort_pending(void) { return abort_pending(); }
 
 int refid_test_conv(int kind, int parity, const void* in0, int C0, const void* in1, int C1, int N, int H, int W,
                     const void* w, long w_rows, int w_cols, int wrows_per_tap, int w_row0, int Cout, const float* bias,

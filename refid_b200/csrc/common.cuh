@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -235,10 +236,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.  a_mn/b_mn: 1 = MN-major operand.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+// Instruction descriptor for kind::f16 with bf16 (format 1) or fp16 (format 0) A/B and fp32 D.  a_mn/b_mn: 1 = MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn, int b_mn, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  return make_idesc_16(M, N, a_mn, b_mn, false);
 }
 
 // exact (erf) GELU and its derivative (reference: nn.GELU(), fusion_modules.py:271)
@@ -259,6 +263,54 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+// ---- storage-type generic conversions -------------------------------------------------------------------------------
+// Activations and packed weights are 16-bit in HBM: bf16 on the training plan, fp16 on the forward-only (inference) plan
+// (11 significant bits instead of 8: the output error against the fp32 reference drops ~7x, which is what the PSNR bar
+// needs).  Pointers stay typed __nv_bfloat16* (a 16-bit container); F16 selects the interpretation.
+template <bool F16>
+__device__ __forceinline__ float cvt_lo(uint32_t u) {
+  if (F16) return __half2float(__ushort_as_half((unsigned short)(u & 0xFFFFu)));
+  return __uint_as_float(u << 16);
+}
+template <bool F16>
+__device__ __forceinline__ float cvt_hi(uint32_t u) {
+  if (F16) return __half2float(__ushort_as_half((unsigned short)(u >> 16)));
+  return __uint_as_float(u & 0xFFFF0000u);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t cvt_pack(float a, float b) {
+  if (F16) {
+    __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// run-time flavoured versions for the memory-bound kernels (warp-uniform branch)
+__device__ __forceinline__ float cvt_lo_rt(uint32_t u, int f16) { return f16 ? cvt_lo<true>(u) : cvt_lo<false>(u); }
+__device__ __forceinline__ float cvt_hi_rt(uint32_t u, int f16) { return f16 ? cvt_hi<true>(u) : cvt_hi<false>(u); }
+__device__ __forceinline__ uint32_t cvt_pack_rt(float a, float b, int f16) {
+  return f16 ? cvt_pack<true>(a, b) : cvt_pack<false>(a, b);
+}
+__device__ __forceinline__ void load8_rt(const __nv_bfloat16* p, float* f, int f16) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  if (f16) {
+    f[0] = cvt_lo<true>(a.x); f[1] = cvt_hi<true>(a.x); f[2] = cvt_lo<true>(a.y); f[3] = cvt_hi<true>(a.y);
+    f[4] = cvt_lo<true>(a.z); f[5] = cvt_hi<true>(a.z); f[6] = cvt_lo<true>(a.w); f[7] = cvt_hi<true>(a.w);
+  } else {
+    f[0] = cvt_lo<false>(a.x); f[1] = cvt_hi<false>(a.x); f[2] = cvt_lo<false>(a.y); f[3] = cvt_hi<false>(a.y);
+    f[4] = cvt_lo<false>(a.z); f[5] = cvt_hi<false>(a.z); f[6] = cvt_lo<false>(a.w); f[7] = cvt_hi<false>(a.w);
+  }
+}
+__device__ __forceinline__ void store8_rt(__nv_bfloat16* p, const float* f, int f16) {
+  uint4 a;
+  if (f16) {
+    a.x = cvt_pack<true>(f[0], f[1]); a.y = cvt_pack<true>(f[2], f[3]); a.z = cvt_pack<true>(f[4], f[5]); a.w = cvt_pack<true>(f[6], f[7]);
+  } else {
+    a.x = cvt_pack<false>(f[0], f[1]); a.y = cvt_pack<false>(f[2], f[3]); a.z = cvt_pack<false>(f[4], f[5]); a.w = cvt_pack<false>(f[6], f[7]);
+  }
+  *reinterpret_cast<uint4*>(p) = a;
 }
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
   const uint4 a = *reinterpret_cast<const uint4*>(p);

@@ -122,6 +122,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   if (BN % seg || (total / seg) > kMaxNBlocks) return 0;
   HaloConvParams& h = out->hp;
   memset(&h, 0, sizeof(h));
+  h.f16 = d.f16;
   h.num_taps = (d.kind == CK_1X1 || up2) ? 1 : 9;
   h.halo = (d.kind == CK_1X1 || up2) ? 0 : 1;
   h.pitch_px = h.halo ? 10 : 8;
@@ -232,6 +233,7 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
   if (fill_taps(d.kind, d.parity, &tt)) return 1;
   TapGemmParams& p = out->p;
   memset(&p, 0, sizeof(p));
+  p.f16 = d.f16;
   REFID_REQUIRE(d.nsrc == 1 || (d.nsrc == 2 && !tt.parity_mode), "build_conv: dual source not allowed with parity views");
   REFID_REQUIRE(d.H % tt.grid_div == 0 && d.W % tt.grid_div == 0, "build_conv: H,W must be even for stride-2 ops");
 

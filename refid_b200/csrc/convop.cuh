@@ -45,6 +45,7 @@ struct ConvDesc {
   int w_cols;
   int wrows_per_tap;
   int w_row0;
+  int f16;  // operands and outputs are fp16 (forward-only plans); 0: bf16
 };
 
 // Build params once (tensor maps are encoded here), launch many times.

@@ -24,11 +24,11 @@ __device__ __forceinline__ float act_mask(float sv, int act, float slope) {
 // input / output-gradient layout conversion
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
-                                                        int T, int Cin, int H, int W, int Kp) {
+                                                        int T, int Cin, int H, int W, int Kp, int f16, int t0, int Tn) {
   pdl_launch_dependents();
   pdl_wait();
   const int G = Kp / 8;
-  const long total = (long)B * T * H * G * W;
+  const long total = (long)B * Tn * H * G * W;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % W);
     long r = idx / W;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict_
     r /= G;
     const int y = (int)(r % H);
     const int n_out = (int)(r / H);
-    const int t = n_out / B, b = n_out % B;
+    const int t = t0 + n_out / B, b = n_out % B;  // time steps [t0, t0+Tn) of the T in the input; output image (t-t0)*B + b
     const float* src = in + ((size_t)(b * T + t) * Cin) * H * W + (size_t)y * W;
     float v[8];
 #pragma unroll
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict_
       const int xx = x + kx - 2;
       v[i] = (kx < 5 && xx >= 0 && xx < W) ? __ldg(src + (size_t)c * H * W + xx) : 0.f;
     }
-    store8(out + (((size_t)n_out * H + y) * W + x) * Kp + g * 8, v);
+    store8_rt(out + (((size_t)n_out * H + y) * W + x) * Kp + g * 8, v, f16);
   }
 }
 
@@ -174,7 +174,7 @@ __device__ __forceinline__ void ln_stats(const float* x, float& mu, float& rstd)
 }
 
 __global__ void __launch_bounds__(kEwThreads) k_ln_fwd(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                       long npix) {
+                                                       long npix, int f16) {
   pdl_launch_dependents();
   pdl_wait();
   const long nvec = npix * 8;
@@ -183,12 +183,12 @@ __global__ void __launch_bounds__(kEwThreads) k_ln_fwd(const __nv_bfloat16* __re
     const long i = it * gridDim.x * blockDim.x + (long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = i < nvec;
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (ok) load8(x + i * 8, v);
+    if (ok) load8_rt(x + i * 8, v, f16);
     float mu, rstd;
     ln_stats(v, mu, rstd);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = (v[k] - mu) * rstd;
-    if (ok) store8(y + i * 8, v);
+    if (ok) store8_rt(y + i * 8, v, f16);
   }
 }
 
@@ -270,6 +270,16 @@ __device__ __forceinline__ void dw_stage_wait() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 }
+__device__ __forceinline__ void lds8_rt(const uint8_t* p, float* f, int f16) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  if (f16) {
+    f[0] = cvt_lo<true>(a.x); f[1] = cvt_hi<true>(a.x); f[2] = cvt_lo<true>(a.y); f[3] = cvt_hi<true>(a.y);
+    f[4] = cvt_lo<true>(a.z); f[5] = cvt_hi<true>(a.z); f[6] = cvt_lo<true>(a.w); f[7] = cvt_hi<true>(a.w);
+    return;
+  }
+  f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
+  f[4] = bf16_lo(a.z); f[5] = bf16_hi(a.z); f[6] = bf16_lo(a.w); f[7] = bf16_hi(a.w);
+}
 __device__ __forceinline__ void lds8(const uint8_t* p, float* f) {
   const uint4 a = *reinterpret_cast<const uint4*>(p);
   f[0] = bf16_lo(a.x); f[1] = bf16_hi(a.x); f[2] = bf16_lo(a.y); f[3] = bf16_hi(a.y);
@@ -280,7 +290,7 @@ __device__ __forceinline__ void lds8(const uint8_t* p, float* f) {
 // [N][dw_pool_parts(H, W)][64] and reduced in a fixed order by k_se_fwd (bit-reproducible forward pass)
 __global__ void __launch_bounds__(kEwThreads, 2) k_dw_fwd(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ d,
-                                                       __nv_bfloat16* __restrict__ g, float* pool, int N, int H, int W) {
+                                                       __nv_bfloat16* __restrict__ g, float* pool, int N, int H, int W, int f16) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ __align__(16) uint8_t patch[kDwPatchBytes];
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(kEwThreads, 2) k_dw_fwd(const __nv_bfloat16* _
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         float v[8];
-        lds8(patch + ((r + ky) * kDwPW + col + kx) * 128 + grp * 16, v);
+        lds8_rt(patch + ((r + ky) * kDwPW + col + kx) * 128 + grp * 16, v, f16);
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] += v[k] * wr[k][ky * 3 + kx];
       }
@@ -323,8 +333,8 @@ __global__ void __launch_bounds__(kEwThreads, 2) k_dw_fwd(const __nv_bfloat16* _
       psum[k] += gv[k];
     }
     const size_t off = (((size_t)n * H + y) * W + x) * 64 + grp * 8;
-    store8(d + off, dg);
-    store8(g + off, gv);
+    if (d) store8_rt(d + off, dg, f16);  // forward-only plans keep no derivative
+    store8_rt(g + off, gv, f16);
   }
   if (pool) {
 #pragma unroll
@@ -507,7 +517,8 @@ __global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, con
 // channel gating
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_gate_fwd(const __nv_bfloat16* __restrict__ gi, const __nv_bfloat16* __restrict__ ge,
-                                                         const float* __restrict__ s, __nv_bfloat16* __restrict__ cs, int N, long hw) {
+                                                         const float* __restrict__ s, __nv_bfloat16* __restrict__ cs, int N, long hw,
+                                                         int f16) {
   pdl_launch_dependents();
   pdl_wait();
   const long nvec = (long)N * hw * 8;
@@ -517,16 +528,16 @@ __global__ void __launch_bounds__(kEwThreads) k_gate_fwd(const __nv_bfloat16* __
     const int n = (int)(pix / hw);
     const float* sc = s + (size_t)n * 64 + grp * 8;
     float a[8], b[8];
-    load8(gi + i * 8, a);
-    load8(ge + i * 8, b);
+    load8_rt(gi + i * 8, a, f16);
+    load8_rt(ge + i * 8, b, f16);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float f = __ldg(sc + k);
       a[k] *= f;
       b[k] *= f;
     }
-    store8(cs + (size_t)pix * 128 + grp * 8, a);
-    store8(cs + (size_t)pix * 128 + 64 + grp * 8, b);
+    store8_rt(cs + (size_t)pix * 128 + grp * 8, a, f16);
+    store8_rt(cs + (size_t)pix * 128 + 64 + grp * 8, b, f16);
   }
 }
 
@@ -604,7 +615,7 @@ __global__ void __launch_bounds__(kEwThreads) k_gate_bwd_apply(const __nv_bfloat
 // weight repacking
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ flat, __nv_bfloat16* __restrict__ wpack,
-                                                     const PackDesc* __restrict__ descs) {
+                                                     const PackDesc* __restrict__ descs, int f16) {
   pdl_launch_dependents();
   pdl_wait();
   const PackDesc d = descs[blockIdx.y];
@@ -616,7 +627,7 @@ __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ f
     long dst = d.dst_off + (d.dst_tap_stride ? (long)t * d.dst_tap_stride + r : i);
     if (d.transpose && d.dst_pitch) dst = d.dst_off + (long)t * (d.dst_tap_stride ? d.dst_tap_stride : per_tap) + (r / d.R) * d.dst_pitch + r % d.R;
     if (d.tapmap[t] < 0) {
-      wpack[dst] = __float2bfloat16(0.f);
+      wpack[dst] = __float2bfloat16(0.f);  // +0 in either format
       continue;
     }
     long src;
@@ -626,7 +637,9 @@ __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ f
     } else {
       src = (long)d.tapmap[t] * per_tap + r;
     }
-    wpack[dst] = __float2bfloat16(flat[d.src_off + src]);
+    const float wv = flat[d.src_off + src];
+    if (f16) reinterpret_cast<__half*>(wpack)[dst] = __float2half_rn(wv);
+    else wpack[dst] = __float2bfloat16(wv);
   }
 }
 
@@ -635,12 +648,15 @@ __global__ void __launch_bounds__(kEwThreads) k_pack(const float* __restrict__ f
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, int H, int W, int Kp, cudaStream_t s) {
+int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, int H, int W, int Kp, cudaStream_t s, int f16,
+                   int t0, int Tn) {
   REFID_REQUIRE(Kp % 32 == 0 && Kp >= 5 * Cin, "unroll5: Kp=%d too small for Cin=%d", Kp, Cin);
-  const long total = (long)B * T * H * W * (Kp / 8);
+  if (Tn < 0) Tn = T;
+  REFID_REQUIRE(t0 >= 0 && t0 + Tn <= T, "unroll5: steps [%d,%d) outside T=%d", t0, t0 + Tn, T);
+  const long total = (long)B * Tn * H * W * (Kp / 8);
   unsigned blocks = blocks_for(total, kEwThreads);
   if (blocks > 148u * 32u) blocks = 148u * 32u;
-  REFID_CUDA_CHECK(launch_k(k_unroll5, dim3(blocks), dim3(kEwThreads), 0, s, in, out, B, T, Cin, H, W, Kp));
+  REFID_CUDA_CHECK(launch_k(k_unroll5, dim3(blocks), dim3(kEwThreads), 0, s, in, out, B, T, Cin, H, W, Kp, f16, t0, Tn));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -701,10 +717,10 @@ int launch_addmask(const AddMaskArgs& a, cudaStream_t s) {
   return 0;
 }
 
-int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s) {
+int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s, int f16) {
   unsigned blocks = blocks_for(npix * 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  REFID_CUDA_CHECK(launch_k(k_ln_fwd, dim3(blocks), dim3(kEwThreads), 0, s, x, y, npix));
+  REFID_CUDA_CHECK(launch_k(k_ln_fwd, dim3(blocks), dim3(kEwThreads), 0, s, x, y, npix, f16));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -719,9 +735,9 @@ int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bf
 }
 
 int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
-                  int N, int H, int W, cudaStream_t s) {
+                  int N, int H, int W, cudaStream_t s, int f16) {
   dim3 grid(dw_pool_parts(H, W), N);
-  REFID_CUDA_CHECK(launch_k(k_dw_fwd, dim3(grid), dim3(kEwThreads), 0, s, a, w, bias, d, g, pool, N, H, W));
+  REFID_CUDA_CHECK(launch_k(k_dw_fwd, dim3(grid), dim3(kEwThreads), 0, s, a, w, bias, d, g, pool, N, H, W, f16));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -755,10 +771,10 @@ int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const
 }
 
 int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const float* s, __nv_bfloat16* cs, int N, long hw,
-                    cudaStream_t st) {
+                    cudaStream_t st, int f16) {
   unsigned blocks = blocks_for((long)N * hw * 8, kEwThreads);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  REFID_CUDA_CHECK(launch_k(k_gate_fwd, dim3(blocks), dim3(kEwThreads), 0, st, gi, ge, s, cs, N, hw));
+  REFID_CUDA_CHECK(launch_k(k_gate_fwd, dim3(blocks), dim3(kEwThreads), 0, st, gi, ge, s, cs, N, hw, f16));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -780,11 +796,12 @@ int launch_gate_bwd_apply(const __nv_bfloat16* gcs, const float* s, const float*
   return 0;
 }
 
-int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_dev, int ndesc, long max_elems, cudaStream_t st) {
+int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_dev, int ndesc, long max_elems, cudaStream_t st,
+                int f16) {
   unsigned bx = blocks_for(max_elems, kEwThreads * 4);
   if (bx > 1024u) bx = 1024u;
   dim3 grid(bx, ndesc);
-  REFID_CUDA_CHECK(launch_k(k_pack, dim3(grid), dim3(kEwThreads), 0, st, flat, wpack, descs_dev));
+  REFID_CUDA_CHECK(launch_k(k_pack, dim3(grid), dim3(kEwThreads), 0, st, flat, wpack, descs_dev, f16));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -2,14 +2,17 @@
 // bias-gradient column sums, masked gradient accumulation, and the pieces of EGACA (event-guided adaptive channel
 // attention, reference basicsr/models/archs/fusion_modules.py:237-333) that are not 1x1 GEMMs: per-pixel LayerNorm,
 // depthwise 3x3 + GELU (+ global pooling), the squeeze-excite MLP and the channel gating.
+// The forward kernels take `f16`: the 16-bit storage is fp16 instead of bf16 (forward-only plans).
 // All activations are NHWC bf16, 16-byte vectorised (8 channels per thread); statistics and parameters are fp32.
 #pragma once
 #include "tapgemm.cuh"
 
 namespace refid {
 
-// fp32 NCHW (frame n_in = b*T + t) -> bf16 NHWC [t*B + b][H][W][Kp], channel k = kx*Cin + c holds in[c][y][x+kx-2].
-int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, int H, int W, int Kp, cudaStream_t s);
+// fp32 NCHW (frame n_in = b*T + t) -> bf16 NHWC [(t-t0)*B + b][H][W][Kp], channel k = kx*Cin + c holds in[c][y][x+kx-2];
+// steps t0 .. t0+Tn-1 (Tn < 0: all T).
+int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, int H, int W, int Kp, cudaStream_t s, int f16 = 0,
+                   int t0 = 0, int Tn = -1);
 // fp32 (B,T,Cv,H,W) -> bf16 [t*B + b][H][W][32] (channels >= Cv zero).
 int launch_gout_pack(const float* gout, __nv_bfloat16* out, int B, int T, int Cv, int H, int W, cudaStream_t s);
 // out[c] += sum_rows in[row][c]   (bf16 [rows][C] contiguous, C % 8 == 0, C <= 256)
@@ -34,7 +37,7 @@ int launch_addmask(const AddMaskArgs& a, cudaStream_t s);
 int launch_sum_series(const __nv_bfloat16* base, long slot_elems, int T, __nv_bfloat16* out, cudaStream_t s);
 
 // Per-pixel LayerNorm over C = 64 channels without affine (the affine is folded into the following 1x1 conv).
-int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s);
+int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s, int f16 = 0);
 // val = d(LN)/dx applied to gy;  dst = (dst_acc ? dst : 0) + add + val   or   dstf += val.
 int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bfloat16* add, __nv_bfloat16* dst, int dst_acc,
                   float* dstf, long npix, cudaStream_t s);
@@ -44,7 +47,7 @@ int launch_ln_bwd(const __nv_bfloat16* x, const __nv_bfloat16* gy, const __nv_bf
 constexpr int kDwTH = 8, kDwTW = 32;  // depthwise-conv pixel tile
 inline int dw_pool_parts(int H, int W) { return ((H + kDwTH - 1) / kDwTH) * ((W + kDwTW - 1) / kDwTW); }
 int launch_dw_fwd(const __nv_bfloat16* a, const float* w, const float* bias, __nv_bfloat16* d, __nv_bfloat16* g, float* pool,
-                  int N, int H, int W, cudaStream_t s);
+                  int N, int H, int W, cudaStream_t s, int f16 = 0);
 // ga = dw^T(gd); gw[c][tap] += sum a[p+tap] gd[p]; gb[c] += sum gd[p].
 int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* w, __nv_bfloat16* ga, float* gw, float* gb,
                   int N, int H, int W, cudaStream_t s);
@@ -68,7 +71,7 @@ int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const
 
 // cs[pix][0:64] = gi*s[n], cs[pix][64:128] = ge*s[n]
 int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const float* s, __nv_bfloat16* cs, int N, long hw,
-                    cudaStream_t st);
+                    cudaStream_t st, int f16 = 0);
 // gs[n][c] += sum_pix gcs[:, c]*gi + gcs[:, 64+c]*ge
 int launch_gate_bwd_reduce(const __nv_bfloat16* gcs, const __nv_bfloat16* gi, const __nv_bfloat16* ge, float* gs, int N,
                            long hw, cudaStream_t st);
@@ -85,6 +88,7 @@ struct PackDesc {
   int dst_pitch;        // transpose mode: elements between destination rows (0: R)
   signed char tapmap[16];  // source tap of destination tap i; -1: zero block
 };
-int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_dev, int ndesc, long max_elems, cudaStream_t st);
+int launch_pack(const float* flat, __nv_bfloat16* wpack, const PackDesc* descs_dev, int ndesc, long max_elems, cudaStream_t st,
+                int f16 = 0);
 
 }  // namespace refid

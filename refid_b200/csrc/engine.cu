@@ -66,6 +66,7 @@ struct Ten {
 struct Series {
   long base = -1;       // byte offset of slot 0 in the workspace
   size_t slot_bytes = 0;
+  int nslots = 0;       // T+1 on a training plan (everything is kept for the backward pass); 1 or 2 on a forward-only plan
   long gbase = -1;      // persistent gradient (dL/dZ) array, allocated when the producing site's wgrad is batched
   bool need_g = false;  // ... or when a deferred gradient needs all T output gradients at once
 };
@@ -119,6 +120,10 @@ struct Engine {
   // plan state
   bool planned = false, dry = false;
   int B = 0, T = 0, H = 0, W = 0, train = 0;
+  int opt_infer_fp16 = 1;  // forward-only plans store activations / packed weights as fp16 (11 significant bits) instead of bf16
+  int opt_graphs = 1;      // replay forward / backward as CUDA graphs
+  int f16 = 0;             // storage flavour of the current plan
+  bool packed_f16 = false;
   char* ws = nullptr;
   float* wmaster = nullptr;
   __nv_bfloat16* wpackb = nullptr;
@@ -142,6 +147,91 @@ struct Engine {
   std::vector<std::vector<ConvOp>> site_calls;  // forward conv calls per site (plan time)
   std::vector<char> site_batched;               // weight/bias gradient of this site is one batched launch
   std::vector<int> site_rep;                    // bit k: input k of the batched site is ONE tensor repeated every step
+
+  // CUDA graphs of the two launch lists.  The plan is static and its buffers fixed; only the caller's tensors (x, event,
+  // out / grad_out) vary between calls, so an instantiated graph is keyed on those pointers.  A key is replayed from its
+  // graph from its second sighting on (the first runs eagerly: one-off pointers are not worth a capture, and every kernel
+  // is loaded and configured before any capture starts); a few graphs per list are kept, least recently used evicted.
+  struct GraphSlot {
+    const void* k[3] = {nullptr, nullptr, nullptr};
+    cudaGraphExec_t exec = nullptr;
+    unsigned long stamp = 0;
+    int seen = 0;
+  };
+  static constexpr int kGraphSlots = 4;
+  GraphSlot fwd_graphs[kGraphSlots], bwd_graphs[kGraphSlots];
+  unsigned long graph_clock = 0;
+  long graph_captures = 0, graph_replays = 0, graph_eager = 0, graph_failures = 0;
+
+  void drop_graphs() {
+    for (GraphSlot* gs : {fwd_graphs, bwd_graphs})
+      for (int i = 0; i < kGraphSlots; ++i) {
+        if (gs[i].exec) cudaGraphExecDestroy(gs[i].exec);
+        gs[i] = GraphSlot();
+      }
+  }
+
+  int run_eager(std::vector<Launch>& ls, bool zero_grads, cudaStream_t st) {
+    if (zero_grads) REFID_CUDA_CHECK(cudaMemsetAsync(gflat, 0, (size_t)flat_floats * 4, st));
+    for (auto& l : ls)
+      if (l(st)) return 1;
+    return 0;
+  }
+
+  int run_list(std::vector<Launch>& ls, GraphSlot* slots, const void* k0, const void* k1, const void* k2, bool zero_grads,
+               cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (!opt_graphs || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      ++graph_eager;  // graphs off, or the caller is capturing this stream itself: plain launches join its capture
+      return run_eager(ls, zero_grads, st);
+    }
+    GraphSlot* hit = nullptr;
+    GraphSlot* lru = &slots[0];
+    for (int i = 0; i < kGraphSlots; ++i) {
+      if (slots[i].seen && slots[i].k[0] == k0 && slots[i].k[1] == k1 && slots[i].k[2] == k2) hit = &slots[i];
+      if (slots[i].stamp < lru->stamp) lru = &slots[i];
+    }
+    if (hit && hit->exec) {
+      hit->stamp = ++graph_clock;
+      ++graph_replays;
+      REFID_CUDA_CHECK(cudaGraphLaunch(hit->exec, st));
+      return 0;
+    }
+    if (!hit) {  // first sighting: remember the key, run eagerly
+      if (lru->exec) cudaGraphExecDestroy(lru->exec);
+      *lru = GraphSlot();
+      lru->k[0] = k0;
+      lru->k[1] = k1;
+      lru->k[2] = k2;
+      lru->seen = 1;
+      lru->stamp = ++graph_clock;
+      ++graph_eager;
+      return run_eager(ls, zero_grads, st);
+    }
+    // second sighting: capture, instantiate, launch
+    hit->stamp = ++graph_clock;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const int rc = run_eager(ls, zero_grads, st);
+      const cudaError_t ee = cudaStreamEndCapture(st, &graph);
+      ok = rc == 0 && ee == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&hit->exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {  // not capturable on this driver: keep working with plain launches (visible in refid_graph_stats)
+      cudaGetLastError();
+      hit->exec = nullptr;
+      opt_graphs = 0;
+      ++graph_failures;
+      ++graph_eager;
+      return run_eager(ls, zero_grads, st);
+    }
+    ++graph_captures;
+    ++graph_replays;
+    REFID_CUDA_CHECK(cudaGraphLaunch(hit->exec, st));
+    return 0;
+  }
 
   // per-call io
   const float* io_x = nullptr;
@@ -344,10 +434,13 @@ struct Engine {
     return (long)off;
   }
 
-  int new_series(size_t slot_bytes) {
+  // Forward-only plans recycle per-step buffers, so the workspace is O(1) in T: a per-step role tensor lives in ONE slot
+  // (it is dead at the end of its step), a recurrent state in two (step t reads slot t-1 and writes slot t, modulo 2).
+  int new_series(size_t slot_bytes, int infer_slots = 1) {
     Series sr;
     sr.slot_bytes = slot_bytes;
-    sr.base = act_alloc(slot_bytes * (size_t)(T + 1));
+    sr.nslots = train ? T + 1 : infer_slots;
+    sr.base = act_alloc(slot_bytes * (size_t)sr.nslots);
     series.push_back(sr);
     return (int)series.size() - 1;
   }
@@ -361,7 +454,7 @@ struct Engine {
     t.pitch = C;
     t.series = sidx;
     t.slot = slot;
-    t.off = series[sidx].base + (long)slot * (long)series[sidx].slot_bytes;
+    t.off = series[sidx].base + (long)(slot % series[sidx].nslots) * (long)series[sidx].slot_bytes;
     tens.push_back(t);
     if (!name.empty()) named[name] = (int)tens.size() - 1;
     return (int)tens.size() - 1;
@@ -647,7 +740,7 @@ struct Engine {
       tens[op.out].act = op.act;
       tens[op.out].slope = op.slope;
       if (op.act == ACT_LRELU) tens[op.out].mask_off = tens[op.out].off;
-      if (op.act == ACT_GELU) tens[op.out].mask_off = act_alloc((size_t)tens[op.out].elems() * 2);
+      if (op.act == ACT_GELU && train) tens[op.out].mask_off = act_alloc((size_t)tens[op.out].elems() * 2);
     }
     else if (op.out >= 0 && !name.empty()) named[name] = op.out;
     if (op.post >= 0 && op.out2 < 0) op.out2 = new_tensor(in0.N, oh, ow, cout, name.empty() ? "" : name + "+");
@@ -671,6 +764,7 @@ struct Engine {
       d.w_cols = cin_total;
       d.wrows_per_tap = cout;
       d.w_row0 = 0;
+      d.f16 = f16;
       if (op.kind == CK_DOWN4) {  // forward of the stride-2 conv runs as a masked 3x3 over the four parity views
         d.kind = CK_DOWN4_HALO;
         d.w_rows = 9L * cout;
@@ -693,7 +787,7 @@ struct Engine {
         const Ten& o = tens[op.out];
         e.out = P(o.off);
         e.C = o.pitch;
-        if (op.act == ACT_GELU) e.out_pre = P(o.mask_off);
+        if (op.act == ACT_GELU && o.mask_off >= 0) e.out_pre = P(o.mask_off);
       }
       e.bias = s.b_off >= 0 ? wmaster + s.b_off : nullptr;
       e.act = op.act;
@@ -881,7 +975,8 @@ struct Engine {
       const __nv_bfloat16 *px = P(tx.off);
       __nv_bfloat16* py = P(tens[y].off);
       cur_label = "";
-      emit([px, py, npix](cudaStream_t s) { return launch_ln_fwd(px, py, npix, s); }, LC_OTHER, 0.0, "ln_fwd");
+      const int h16 = f16;
+      emit([px, py, npix, h16](cudaStream_t s) { return launch_ln_fwd(px, py, npix, s, h16); }, LC_OTHER, 0.0, "ln_fwd");
     }
     if (train) {
       Engine* self = this;
@@ -913,14 +1008,15 @@ struct Engine {
     const Site s = sites[site_id];
     const int g = new_tensor(ta.N, ta.H, ta.W, ta.C, name);
     tens[g].act = ACT_GELU;
-    tens[g].mask_off = act_alloc((size_t)ta.elems() * 2);
+    if (train) tens[g].mask_off = act_alloc((size_t)ta.elems() * 2);
     {
       const __nv_bfloat16* pa = P(ta.off);
-      __nv_bfloat16 *pd = P(tens[g].mask_off), *pg = P(tens[g].off);
+      __nv_bfloat16 *pd = train ? P(tens[g].mask_off) : nullptr, *pg = P(tens[g].off);
+      const int h16 = f16;
       const float *w = wmaster + s.w_off, *b = wmaster + s.b_off;
       float* pool = pool_off >= 0 ? PF(pool_off) : nullptr;
       const int N = ta.N, Hh = ta.H, Ww = ta.W;
-      emit([pa, w, b, pd, pg, pool, N, Hh, Ww](cudaStream_t st) { return launch_dw_fwd(pa, w, b, pd, pg, pool, N, Hh, Ww, st); }, LC_OTHER, 0.0, "dw_fwd");
+      emit([pa, w, b, pd, pg, pool, N, Hh, Ww, h16](cudaStream_t st) { return launch_dw_fwd(pa, w, b, pd, pg, pool, N, Hh, Ww, st, h16); }, LC_OTHER, 0.0, "dw_fwd");
     }
     if (train) {
       Engine* self = this;
@@ -982,7 +1078,8 @@ struct Engine {
       const __nv_bfloat16 *pgi = P(tens[g_i].off), *pge = P(tens[g_e].off);
       __nv_bfloat16* pcs = P(tens[cs].off);
       emit([pool, parts, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, parts, inv_hw, sp, sg, mean, z, N, st); }, LC_OTHER, 0.0, "se_fwd");
-      emit([pgi, pge, sg, pcs, N, hw](cudaStream_t st) { return launch_gate_fwd(pgi, pge, sg, pcs, N, hw, st); }, LC_OTHER, 0.0, "gate_fwd");
+      const int h16 = f16;
+      emit([pgi, pge, sg, pcs, N, hw, h16](cudaStream_t st) { return launch_gate_fwd(pgi, pge, sg, pcs, N, hw, st, h16); }, LC_OTHER, 0.0, "gate_fwd");
     }
     if (train) {
       Engine* self = this;
@@ -1090,7 +1187,8 @@ struct Engine {
     {
       __nv_bfloat16* o = P(tens[ximg].off);
       const int Bc = B, Cin = cfg.img_chn, Hh = H, Ww = W, Kp = Kp_img;
-      emit([self, o, Bc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_x, o, Bc, 1, Cin, Hh, Ww, Kp, st); }, LC_OTHER, 0.0, "unroll5");
+      const int h16 = f16;
+      emit([self, o, Bc, Cin, Hh, Ww, Kp, h16](cudaStream_t st) { return launch_unroll5(self->io_x, o, Bc, 1, Cin, Hh, Ww, Kp, st, h16); }, LC_OTHER, 0.0, "unroll5");
     }
     ConvOp hi;
     hi.kind = CK_ROWS5;
@@ -1134,29 +1232,61 @@ struct Engine {
       mark_f32acc(xb[l]);
       f = xb[l];
     }
-    // ---- event head over all T slices at once, then both directions' level-0 in-convs (recurrence independent)
-    const int xev = new_tensor(T * B, H, W, Kp_ev);
-    tens[xev].need_grad = false;
-    {
-      __nv_bfloat16* o = P(tens[xev].off);
-      const int Bc = B, Tc = T, Cin = cfg.ev_chn, Hh = H, Ww = W, Kp = Kp_ev;
-      emit([self, o, Bc, Tc, Cin, Hh, Ww, Kp](cudaStream_t st) { return launch_unroll5(self->io_ev, o, Bc, Tc, Cin, Hh, Ww, Kp, st); }, LC_OTHER, 0.0, "unroll5");
+    // ---- event head + both directions' level-0 in-convs (recurrence independent): ONE launch each over all T slices on a
+    //      training plan; step by step on a forward-only plan, where only u0 (both directions' conv outputs) is kept for
+    //      all T and the unrolled input / head output live in one-step buffers (workspace O(1) in T apart from u0)
+    int u0_all = -1;
+    if (train) {
+      const int xev = new_tensor(T * B, H, W, Kp_ev);
+      tens[xev].need_grad = false;
+      {
+        __nv_bfloat16* o = P(tens[xev].off);
+        const int Bc = B, Tc = T, Cin = cfg.ev_chn, Hh = H, Ww = W, Kp = Kp_ev;
+        const int h16 = f16;
+        emit([self, o, Bc, Tc, Cin, Hh, Ww, Kp, h16](cudaStream_t st) { return launch_unroll5(self->io_ev, o, Bc, Tc, Cin, Hh, Ww, Kp, st, h16); }, LC_OTHER, 0.0, "unroll5");
+      }
+      ConvOp he;
+      he.kind = CK_ROWS5;
+      he.site = site("head");
+      he.in[0] = xev;
+      he.act = ACT_LRELU;
+      he.slope = 0.2f;
+      const int e_all = conv(he, "e_all");
+      if (e_all < 0) return 1;
+      ConvOp cu;
+      cu.site = site("enc0_in");
+      cu.in[0] = e_all;
+      cu.act = ACT_LRELU;
+      cu.slope = 0.04f;  // ConvLayer's LeakyReLU(0.2) applied twice (recurrent_sub_modules.py:283-285)
+      u0_all = conv(cu, "u0_all");
+      if (u0_all < 0) return 1;
+    } else {
+      u0_all = new_tensor(T * B, H, W, 4 * b, "u0_all");
+      const int xev = new_tensor(B, H, W, Kp_ev);
+      const int e_t = new_tensor(B, H, W, b);
+      tens[e_t].act = ACT_LRELU;
+      tens[e_t].slope = 0.2f;
+      for (int t = 0; t < T; ++t) {
+        __nv_bfloat16* o = P(tens[xev].off);
+        const int Bc = B, Tc = T, Cin = cfg.ev_chn, Hh = H, Ww = W, Kp = Kp_ev, h16 = f16;
+        emit([self, o, Bc, Tc, Cin, Hh, Ww, Kp, h16, t](cudaStream_t st) { return launch_unroll5(self->io_ev, o, Bc, Tc, Cin, Hh, Ww, Kp, st, h16, t, 1); }, LC_OTHER, 0.0, "unroll5");
+        ConvOp he;
+        he.kind = CK_ROWS5;
+        he.site = site("head");
+        he.in[0] = xev;
+        he.out = e_t;
+        he.act = ACT_LRELU;
+        he.slope = 0.2f;
+        if (conv(he) < 0) return 1;
+        ConvOp cu;
+        cu.site = site("enc0_in");
+        cu.in[0] = e_t;
+        cu.out = view(u0_all, t * B, B, 0, 4 * b);
+        cu.act = ACT_LRELU;
+        cu.slope = 0.04f;
+        if (conv(cu) < 0) return 1;
+      }
     }
-    ConvOp he;
-    he.kind = CK_ROWS5;
-    he.site = site("head");
-    he.in[0] = xev;
-    he.act = ACT_LRELU;
-    he.slope = 0.2f;
-    const int e_all = conv(he, "e_all");
-    if (e_all < 0) return 1;
-    ConvOp cu;
-    cu.site = site("enc0_in");
-    cu.in[0] = e_all;
-    cu.act = ACT_LRELU;
-    cu.slope = 0.04f;  // ConvLayer's LeakyReLU(0.2) applied twice (recurrent_sub_modules.py:283-285)
-    const int u0_all = conv(cu, "u0_all");
-    if (u0_all < 0) return 1;
     // ---- EGACA image branch, once per direction (image feature is constant over time)
     int g_i[2];
     for (int d = 0; d < 2; ++d) {
@@ -1175,7 +1305,7 @@ struct Engine {
     // ---- backward sweep t = T-1 .. 0 (XXNet_final_attenfusion_arch.py:172-181)
     // Recurrent states live in (T+1)-slot series: slot t = h_t, the spare slot is the zero initial state.
     auto state_series = [&](int Hh, int Ww, int C, int pad_slot, int* pad_tensor) {
-      const int sidx = new_series((size_t)B * Hh * Ww * C * 2);
+      const int sidx = new_series((size_t)B * Hh * Ww * C * 2, 2);
       *pad_tensor = series_tensor(sidx, pad_slot, B, Hh, Ww, C);
       tens[*pad_tensor].need_grad = false;
       zero_fwd.push_back({(size_t)tens[*pad_tensor].off, (size_t)tens[*pad_tensor].elems() * 2});
@@ -1239,7 +1369,7 @@ struct Engine {
     int hf[3], sd[3], hf_series[3], sd_series[3];
     for (int l = 0; l < 3; ++l) hf_series[l] = state_series(H >> l, W >> l, (2 * b) << l, 0, &hf[l]);
     for (int i = 0; i < 3; ++i) sd_series[i] = state_series(H >> (2 - i), W >> (2 - i), (4 * b) >> i, 0, &sd[i]);
-    const int sp_all = new_tensor(T * B, H, W, b, "sp_all");
+    const int sp_all = train ? new_tensor(T * B, H, W, b, "sp_all") : -1;  // pred's input for all T steps (batched pred backward)
     for (int t = 0; t < T; ++t) {
       cur_slot = t + 1;
       cur_sdir = "f";
@@ -1324,7 +1454,7 @@ struct Engine {
           post = dn[1 - i];
         } else {
           post = head;
-          preset = view(sp_all, t * B, B, 0, b);
+          if (train) preset = view(sp_all, t * B, B, 0, b);
         }
         const int s = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2,
                             series_tensor(sd_series[i], t + 1, B, H >> (2 - i), W >> (2 - i), (4 * b) >> i));
@@ -1552,6 +1682,8 @@ struct Engine {
     W = W_;
     train = train_;
     dry = dry_;
+    f16 = (!train && opt_infer_fp16) ? 1 : 0;
+    if (!dry) drop_graphs();
     ws = static_cast<char*>(workspace);
     wmaster = static_cast<float*>(wpack);
     wpackb = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(wpack) + align_up((size_t)flat_floats * 4, 1024));
@@ -1622,6 +1754,7 @@ int refid_destroy(refid_handle h) {
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!e) return 0;
   if (e->packs_dev) cudaFree(e->packs_dev);
+  e->drop_graphs();
   delete e;
   return 0;
 }
@@ -1678,7 +1811,7 @@ int refid_pack_weights(refid_handle h, const float* flat, void* stream) {
     REFID_CUDA_CHECK(cudaMemcpy(e->packs_dev, e->packs.data(), e->packs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
   }
   REFID_CUDA_CHECK(cudaMemcpyAsync(e->wmaster, flat, (size_t)e->flat_floats * 4, cudaMemcpyDeviceToDevice, st));
-  return launch_pack(flat, e->wpackb, e->packs_dev, (int)e->packs.size(), e->pack_max, st);
+  return launch_pack(flat, e->wpackb, e->packs_dev, (int)e->packs.size(), e->pack_max, st, e->f16);
 }
 
 int refid_forward(refid_handle h, const float* x, const float* event, float* out, void* stream) {
@@ -1686,13 +1819,11 @@ int refid_forward(refid_handle h, const float* x, const float* event, float* out
   Engine* e = reinterpret_cast<Engine*>(h);
   REFID_REQUIRE(e->planned, "refid_forward: no plan");
   REFID_REQUIRE(x && event && out, "refid_forward: null tensor");
+  REFID_REQUIRE_HEALTHY("refid_forward");
   e->io_x = x;
   e->io_ev = event;
   e->io_out = out;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (auto& l : e->fwd)
-    if (l(st)) return 1;
-  return 0;
+  return e->run_list(e->fwd, e->fwd_graphs, x, event, out, false, static_cast<cudaStream_t>(stream));
 }
 
 int refid_backward(refid_handle h, const float* grad_out, void* stream) {
@@ -1700,13 +1831,39 @@ int refid_backward(refid_handle h, const float* grad_out, void* stream) {
   Engine* e = reinterpret_cast<Engine*>(h);
   REFID_REQUIRE(e->planned && e->train, "refid_backward: no training plan");
   REFID_REQUIRE(grad_out, "refid_backward: null tensor");
+  REFID_REQUIRE_HEALTHY("refid_backward");
   e->io_gout = grad_out;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  REFID_CUDA_CHECK(cudaMemsetAsync(e->gflat, 0, (size_t)e->flat_floats * 4, st));
-  for (auto& l : e->bwd)
-    if (l(st)) return 1;
+  return e->run_list(e->bwd, e->bwd_graphs, grad_out, nullptr, nullptr, true, static_cast<cudaStream_t>(stream));
+}
+
+int refid_set_option(refid_handle h, const char* name, long value) {
+  using namespace refid;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  REFID_REQUIRE(e && name, "refid_set_option: null argument");
+  const std::string n(name);
+  if (n == "infer_fp16") {
+    REFID_REQUIRE(!e->planned, "refid_set_option: infer_fp16 must be set before refid_plan");
+    e->opt_infer_fp16 = value ? 1 : 0;
+  } else if (n == "graphs") {
+    e->opt_graphs = value ? 1 : 0;
+    if (!value) e->drop_graphs();
+  } else {
+    set_error("refid_set_option: unknown option '%s'", name);
+    return 1;
+  }
   return 0;
 }
+
+int refid_graph_stats(refid_handle h, long out[4]) {
+  Engine* e = reinterpret_cast<Engine*>(h);
+  out[0] = e->graph_captures;
+  out[1] = e->graph_replays;
+  out[2] = e->graph_eager;
+  out[3] = e->graph_failures;
+  return 0;
+}
+
+int refid_plan_storage(refid_handle h) { return reinterpret_cast<Engine*>(h)->f16; }
 
 // Re-runs forward (+ backward) of the current plan on the last call's tensors with a CUDA event pair around every
 // launch and sums device time, launch count and algorithmic FLOPs per launch class

@@ -40,6 +40,7 @@ struct HaloConvParams {
   int num_items;                  // tiles * n_blocks
   int resident_b;                 // weights stay in shared memory for the whole kernel (n_blocks == 1)
   int stages_a, stages_b;
+  int f16;  // activations / packed weights are fp16 (forward-only plans) instead of bf16
 };
 
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);

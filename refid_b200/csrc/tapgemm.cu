@@ -7,32 +7,35 @@ namespace {
 
 constexpr int kThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-5: epilogue
 
+template <bool F16>
 __device__ __forceinline__ void load16(const __nv_bfloat16* p, float* f) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = q[0], b = q[1];
   uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    f[2 * i] = bf16_lo(w[i]);
-    f[2 * i + 1] = bf16_hi(w[i]);
+    f[2 * i] = cvt_lo<F16>(w[i]);
+    f[2 * i + 1] = cvt_hi<F16>(w[i]);
   }
 }
+template <bool F16>
 __device__ __forceinline__ void store16(__nv_bfloat16* p, const float* f) {
   uint4 a, b;
-  a.x = pack_bf16(f[0], f[1]);
-  a.y = pack_bf16(f[2], f[3]);
-  a.z = pack_bf16(f[4], f[5]);
-  a.w = pack_bf16(f[6], f[7]);
-  b.x = pack_bf16(f[8], f[9]);
-  b.y = pack_bf16(f[10], f[11]);
-  b.z = pack_bf16(f[12], f[13]);
-  b.w = pack_bf16(f[14], f[15]);
+  a.x = cvt_pack<F16>(f[0], f[1]);
+  a.y = cvt_pack<F16>(f[2], f[3]);
+  a.z = cvt_pack<F16>(f[4], f[5]);
+  a.w = cvt_pack<F16>(f[6], f[7]);
+  b.x = cvt_pack<F16>(f[8], f[9]);
+  b.y = cvt_pack<F16>(f[10], f[11]);
+  b.z = cvt_pack<F16>(f[12], f[13]);
+  b.w = cvt_pack<F16>(f[14], f[15]);
   uint4* q = reinterpret_cast<uint4*>(p);
   q[0] = a;
   q[1] = b;
 }
 
 // Epilogue of 16 consecutive output channels [c0, c0+16) of one pixel (see EpiDesc in tapgemm.cuh).
+template <bool F16>
 __device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const float* bias, size_t base, int c0, int n, int y,
                                             int x) {
   if (bias) {
@@ -41,19 +44,19 @@ __device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const fl
   }
   if (e.pre) {
     float t[16];
-    load16(e.pre + base + c0, t);
+    load16<F16>(e.pre + base + c0, t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += t[i];
   }
   if (e.pre2) {
     float t[16];
-    load16(e.pre2 + base + c0, t);
+    load16<F16>(e.pre2 + base + c0, t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += t[i];
   }
   if (e.sv) {
     float t[16];
-    load16(e.sv + base + c0, t);
+    load16<F16>(e.sv + base + c0, t);
     if (e.act == ACT_MULT) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] *= t[i];
@@ -67,9 +70,9 @@ __device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const fl
       float dg[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) gelu_both_f(v[i], &v[i], &dg[i]);
-      if (e.out_pre) store16(e.out_pre + base + c0, dg);
+      if (e.out_pre) store16<F16>(e.out_pre + base + c0, dg);
     } else {
-      if (e.out_pre) store16(e.out_pre + base + c0, v);
+      if (e.out_pre) store16<F16>(e.out_pre + base + c0, v);
       if (e.act == ACT_LRELU) {
         const float sl = e.slope;
 #pragma unroll
@@ -77,7 +80,7 @@ __device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const fl
       }
     }
   }
-  if (e.out) store16(e.out + base + c0, v);
+  if (e.out) store16<F16>(e.out + base + c0, v);
   if (e.out_nchw && c0 == 0) {
     float* o = e.out_nchw + (size_t)n * e.nchw_nstride + (size_t)(y * e.osy + e.ooy) * e.OW + (size_t)(x * e.osx + e.oox);
     const size_t plane = (size_t)e.OH * e.OW;
@@ -99,14 +102,14 @@ __device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const fl
   }
   if (e.out2) {
     float t[16];
-    load16(e.post + base + c0, t);
+    load16<F16>(e.post + base + c0, t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) t[i] += v[i];
-    store16(e.out2 + base + c0, t);
+    store16<F16>(e.out2 + base + c0, t);
   }
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   constexpr int A_BYTES = 128 * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   constexpr uint32_t SWZ = (BK == 64) ? 2u : 4u;    // UMMA layout type: 128B / 64B swizzle
   constexpr uint32_t SBO = 8u * BK * 2u;            // 8 rows of one swizzle span
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
+  constexpr uint32_t IDESC = make_idesc_16(128, BN, 0, 0, F16);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (valid) epi_apply16(e, v, bias, base, c0, n, y, x);
+      if (valid) epi_apply16<F16>(e, v, bias, base, c0, n, y, x);
     }
   }
 
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   }
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool F16>
 int launch_inst(TapGemmParams& p, int n_blocks, cudaStream_t stream) {
   constexpr int STAGE_BYTES = 128 * BK * 2 + BN * BK * 2;
   const int total_slabs = p.src_slabs[0] + (p.nsrc > 1 ? p.src_slabs[1] : 0);
@@ -246,12 +249,12 @@ int launch_inst(TapGemmParams& p, int n_blocks, cudaStream_t stream) {
   const size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
   static int configured = 0;  // per instantiation
   if (configured < (int)smem) {
-    REFID_CUDA_CHECK(cudaFuncSetAttribute(tapgemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(tapgemm_kernel<BN, BK, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
   const int tiles = p.tiles_x * p.tiles_y * ((p.N + p.TN - 1) / p.TN);
   dim3 grid(tiles, n_blocks);
-  REFID_CUDA_CHECK(launch_k(tapgemm_kernel<BN, BK>, dim3(grid), dim3(kThreads), smem, stream, p));
+  REFID_CUDA_CHECK(launch_k(tapgemm_kernel<BN, BK, F16>, dim3(grid), dim3(kThreads), smem, stream, p));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -280,7 +283,7 @@ int launch_tapgemm(TapGemmParams& p, int BN, int BK, int n_blocks, cudaStream_t 
   REFID_REQUIRE(p.num_taps >= 1 && p.num_taps <= kMaxTaps, "tapgemm: bad num_taps %d", p.num_taps);
   REFID_REQUIRE(p.TW * p.TH * p.TN == 128, "tapgemm: tile %dx%dx%d != 128", p.TW, p.TH, p.TN);
 #define INST(bn, bk) \
-  if (BN == bn && BK == bk) return launch_inst<bn, bk>(p, n_blocks, stream);
+  if (BN == bn && BK == bk) return p.f16 ? launch_inst<bn, bk, true>(p, n_blocks, stream) : launch_inst<bn, bk, false>(p, n_blocks, stream);
   INST(32, 32) INST(64, 32) INST(128, 32) INST(256, 32)
   INST(32, 64) INST(64, 64) INST(128, 64) INST(256, 64)
 #undef INST

@@ -58,6 +58,7 @@ struct TapGemmParams {
   int TW, TH, TN, tiles_x, tiles_y;
   int N, H, W;  // output-grid extent
   int num_stages;
+  int f16;  // fp16 instead of bf16 storage (forward-only plans)
 };
 
 // Host: geometry helper -- picks TW x TH x TN = 128 for an (N,H,W) grid.

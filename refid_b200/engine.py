@@ -42,6 +42,9 @@ def _bind(L):
     L.refid_profile.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.refid_profile_csv.argtypes = [c_void_p, c_int, ctypes.c_char_p, c_void_p]
     L.refid_num_launches.argtypes = [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    L.refid_set_option.argtypes = [c_void_p, ctypes.c_char_p, c_long]
+    L.refid_graph_stats.argtypes = [c_void_p, ctypes.POINTER(c_long * 4)]
+    L.refid_plan_storage.argtypes = [c_void_p]
     L.refid_debug_tensor.argtypes = [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p)] + [ctypes.POINTER(c_int)] * 5
     L._refid_bound = True
     return L
@@ -73,33 +76,56 @@ class Engine:
         except Exception:  # interpreter shutdown
             pass
 
+    def set_option(self, name, value):
+        """Engine option (include/refid_b200.h): "infer_fp16" (before plan), "graphs"."""
+        _lib.check(self.L.refid_set_option(self.h, name.encode(), int(value)), "refid_set_option")
+
+    def graph_stats(self):
+        a = (c_long * 4)()
+        self.L.refid_graph_stats(self.h, ctypes.byref(a))
+        return {"captures": a[0], "replays": a[1], "eager": a[2], "failures": a[3]}
+
+    def storage(self):
+        """16-bit storage type of the current plan's activations / packed weights."""
+        return torch.float16 if self.L.refid_plan_storage(self.h) else torch.bfloat16
+
     def workspace_bytes(self, B, T, H, W, train):
         n = c_size_t(0)
         _lib.check(self.L.refid_workspace_bytes(self.h, B, T, H, W, int(train), ctypes.byref(n)), "refid_workspace_bytes")
         return n.value
 
     def plan(self, B, T, H, W, train, workspace, wpack, grad_flat):
+        with torch.cuda.device(workspace.device):
+            self._plan(B, T, H, W, train, workspace, wpack, grad_flat)
+
+    def _plan(self, B, T, H, W, train, workspace, wpack, grad_flat):
         _lib.check(self.L.refid_plan(self.h, B, T, H, W, int(train), _lib.ptr(workspace), _lib.ptr(wpack),
                                      _lib.ptr(grad_flat)), "refid_plan")
         self.shape = (B, T, H, W, bool(train))
         self._keep = (workspace, wpack, grad_flat)  # the plan holds raw pointers into these
 
-    @staticmethod
-    def _stream():
-        return c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        # the stream of the device the plan's buffers live on (not of whatever device happens to be current)
+        return c_void_p(torch.cuda.current_stream(self._keep[0].device).cuda_stream)
 
     def pack_weights(self, flat):
         assert flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() == self.flat_floats
+        with torch.cuda.device(flat.device):
+            self._pack_weights(flat)
+
+    def _pack_weights(self, flat):
         _lib.check(self.L.refid_pack_weights(self.h, _lib.ptr(flat), self._stream()), "refid_pack_weights")
 
     def forward(self, x, event, out):
         for t in (x, event, out):
             assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
-        _lib.check(self.L.refid_forward(self.h, _lib.ptr(x), _lib.ptr(event), _lib.ptr(out), self._stream()), "refid_forward")
+        with torch.cuda.device(x.device):
+            _lib.check(self.L.refid_forward(self.h, _lib.ptr(x), _lib.ptr(event), _lib.ptr(out), self._stream()), "refid_forward")
 
     def backward(self, grad_out):
         assert grad_out.dtype == torch.float32 and grad_out.is_contiguous() and grad_out.is_cuda
-        _lib.check(self.L.refid_backward(self.h, _lib.ptr(grad_out), self._stream()), "refid_backward")
+        with torch.cuda.device(grad_out.device):
+            _lib.check(self.L.refid_backward(self.h, _lib.ptr(grad_out), self._stream()), "refid_backward")
 
     def profile(self, with_backward=True):
         """Per-class device time / algorithmic FLOPs / launch count of one forward(+backward) replay (see header)."""
@@ -126,6 +152,6 @@ class Engine:
         ws = self._keep[0]
         off = p.value - ws.data_ptr()
         n = ((N * H * W - 1) * pitch + C) * 2
-        raw = ws[off:off + n].view(torch.bfloat16)
+        raw = ws[off:off + n].view(self.storage())
         t = torch.as_strided(raw, (N, H, W, C), (H * W * pitch, W * pitch, pitch, 1))
         return t.float().permute(0, 3, 1, 2).contiguous()

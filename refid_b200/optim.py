@@ -30,6 +30,7 @@ class _ClipAdamBase(torch.optim.Optimizer):
         self._norm = None
         self._tables = None
         self._steps = None
+        self._step_params = None
 
     def clip_grad_norm_(self, max_norm):
         """Global 2-norm clip of all gradients to `max_norm`, fused into the next step()."""
@@ -40,10 +41,11 @@ class _ClipAdamBase(torch.optim.Optimizer):
         return self._norm
 
     def _sync_steps(self):
-        if getattr(self, "_tables", None) is not None:
-            groups = [g for g in self.param_groups if len(g["params"]) > 0]
-            for p, k in zip(groups[0]["params"], self._steps):
-                self.state[p]["step"].fill_(float(k))
+        """Host step counts -> the `step` tensors of torch's state layout (before the state is exported or re-read)."""
+        if getattr(self, "_tables", None) is not None and self._step_params is not None:
+            for p, k in zip(self._step_params, self._steps):
+                if p in self.state and "step" in self.state[p]:
+                    self.state[p]["step"].fill_(float(k))
 
     def state_dict(self):
         self._sync_steps()
@@ -66,6 +68,9 @@ class _ClipAdamBase(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        # The reference builds two groups (`optim_params`, and `optim_params_lowlr` for names no parameter of this network
+        # has -- empty, with its own lr; twoImage_event_recurrent_model.py:67-91).  Empty groups are carried through
+        # state_dict()/load_state_dict() untouched so optimizer checkpoints interchange; the step runs on the non-empty one.
         groups = [g for g in self.param_groups if len(g["params"]) > 0]
         if len(groups) != 1:
             raise NotImplementedError("one non-empty parameter group (the reference's option files produce exactly one)")
@@ -78,6 +83,7 @@ class _ClipAdamBase(torch.optim.Optimizer):
             for p in params:
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                     raise RuntimeError("ClipAdamW needs contiguous fp32 CUDA parameters (no CPU path)")
+            self._sync_steps()  # the tables are about to be rebuilt from the `step` tensors: make them current first
             if self._handle is not None:
                 _lib.check(L.refid_optim_destroy(self._handle), "refid_optim_destroy")
             numel = (ctypes.c_long * n)(*[p.numel() for p in params])
@@ -98,11 +104,12 @@ class _ClipAdamBase(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             VP = ctypes.c_void_p * n
             self._steps = [int(self.state[p]["step"].item()) for p in params]
+            self._step_params = list(params)
             self._tables = (VP, VP(*[p.data_ptr() for p in params]), VP(*[self.state[p]["exp_avg"].data_ptr() for p in params]),
                             VP(*[self.state[p]["exp_avg_sq"].data_ptr() for p in params]))
-            L.refid_optim_step.argtypes = [ctypes.c_void_p, VP, VP, VP, VP, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                           ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_long * n, ctypes.c_int,
-                                           ctypes.c_void_p, ctypes.c_void_p]
+            # pointer-typed (not array-size-typed) prototype: optimizers over different tensor counts coexist
+            L.refid_optim_step.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 4 + [ctypes.c_float] * 6 + \
+                                          [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         VP, a_p, a_m, a_v = self._tables
         keep, ptrs, steps = [], [], self._steps
         for i, p in enumerate(params):
@@ -121,9 +128,12 @@ class _ClipAdamBase(torch.optim.Optimizer):
         a_steps = (ctypes.c_long * n)(*steps)
         stream = ctypes.c_void_p(torch.cuda.current_stream(params[0].device).cuda_stream)
         with torch.cuda.device(params[0].device):
-            _lib.check(L.refid_optim_step(self._handle, a_p, a_g, a_m, a_v, self._max_norm, g["lr"], g["betas"][0], g["betas"][1],
-                                          g["eps"], g["weight_decay"], a_steps, 1 if self._decoupled else 0,
-                                          _lib.ptr(self._norm), stream), "refid_optim_step")
+            cast = lambda a: ctypes.cast(a, ctypes.c_void_p)
+            _lib.check(L.refid_optim_step(self._handle, cast(a_p), cast(a_g), cast(a_m), cast(a_v), self._max_norm, g["lr"],
+                                          g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], cast(a_steps),
+                                          1 if self._decoupled else 0, _lib.ptr(self._norm), stream), "refid_optim_step")
+        # the kernel wrote the parameters through raw pointers: tell autograd / the engine's packed-weight cache
+        torch.autograd.graph.increment_version([p for p, q in zip(params, ptrs) if q is not None])
         self._max_norm = 0.0  # like the reference, the clip is requested before every step
         return loss
 

@@ -14,6 +14,7 @@ from copy import deepcopy
 
 import torch
 
+from . import _lib
 from . import losses as loss_module
 from . import optim
 from .plugin import define_network
@@ -39,11 +40,17 @@ class TwoImageEventRecurrentRestorationModel:
             og = train_opt.get("optim_g", {"type": "AdamW", "lr": 2e-4, "weight_decay": 1e-4, "betas": [0.9, 0.99]})
             og = dict(og)
             optim_type = og.pop("type")
-            params = [p for p in self.net_g.parameters() if p.requires_grad]
+            # the reference's two groups (:67-91): every parameter of this network lands in the first; the second
+            # (`module.offsets` / `module.dcns` names, lr x 0.1) is empty but part of the optimizer's state_dict layout
+            optim_params, optim_params_lowlr = [], []
+            for k, v in self.net_g.named_parameters():
+                if v.requires_grad:
+                    (optim_params_lowlr if k.startswith(("module.offsets", "module.dcns")) else optim_params).append(v)
+            groups = [{"params": optim_params}, {"params": optim_params_lowlr, "lr": og["lr"] * 0.1}]
             if optim_type == "AdamW":
-                self.optimizer_g = optim.ClipAdamW(params, **og)
+                self.optimizer_g = optim.ClipAdamW(groups, **og)
             elif optim_type == "Adam":
-                self.optimizer_g = optim.ClipAdam(params, **og)
+                self.optimizer_g = optim.ClipAdam(groups, **og)
             else:
                 raise NotImplementedError(f"optimizer {optim_type} is not supperted yet.")
         self.log_dict = {}
@@ -64,6 +71,7 @@ class TwoImageEventRecurrentRestorationModel:
             self.optimizer_g.clip_grad_norm_(0.01)  # :304-306, fused into the step below
         self.optimizer_g.step()
         self.log_dict = {"l_pix": l_pix.detach()}
+        _lib.raise_if_aborted()  # a kernel that hit its bounded wait invalidates everything after it: fail loudly
         return l_pix.detach()
 
     def test(self):
@@ -77,5 +85,6 @@ class TwoImageEventRecurrentRestorationModel:
                 outs.append(self.net_g(x=self.lq[i:j], event=self.voxel[i:j]))
                 i = j
             self.output = torch.cat(outs, dim=0)
+        _lib.raise_if_aborted()
         self.net_g.train()
         return self.output

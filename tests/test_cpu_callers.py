@@ -36,6 +36,41 @@ def test_clip_adam_constructor_and_state_layout():
     assert sd["param_groups"][0]["lr"] == 2e-4
 
 
+def test_optimizer_state_interchanges_with_the_reference_group_layout():
+    """The reference builds AdamW over TWO groups, the second (`optim_params_lowlr`, lr x 0.1) empty for this network
+    (twoImage_event_recurrent_model.py:67-91).  A state_dict produced by that layout loads into the mirror's optimizer and
+    the mirror's state_dict loads into a reference-shaped torch optimizer (resuming from a reference .state)."""
+    from refid_b200 import plugin, recurrent_model
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    opt = plugin.load_options(os.path.join(root, "options/train/GoPro_blurry_11p1_b200.yml"))
+    m = recurrent_model.TwoImageEventRecurrentRestorationModel(opt, device="cpu")
+    ours = m.optimizer_g
+    assert [len(g["params"]) for g in ours.param_groups] == [183, 0]
+    assert ours.param_groups[1]["lr"] == pytest.approx(ours.param_groups[0]["lr"] * 0.1)
+    params = [p for p in m.net_g.parameters()]
+    og = dict(opt["train"]["optim_g"])
+    og.pop("type")
+    ref = torch.optim.AdamW([{"params": params}, {"params": [], "lr": og["lr"] * 0.1}], **og)  # the reference's call
+    for p in params[:5]:  # a few populated states, as after training steps
+        ref.state[p] = {"step": torch.tensor(7.0), "exp_avg": torch.full_like(p, 0.5), "exp_avg_sq": torch.full_like(p, 0.25)}
+    ours.load_state_dict(ref.state_dict())
+    st = ours.state[params[0]]
+    assert float(st["step"]) == 7.0 and torch.equal(st["exp_avg"], torch.full_like(params[0], 0.5))
+    ref2 = torch.optim.AdamW([{"params": params}, {"params": [], "lr": og["lr"] * 0.1}], **og)
+    ref2.load_state_dict(ours.state_dict())  # and back
+    assert float(ref2.state[params[4]]["step"]) == 7.0
+    assert [len(g["params"]) for g in ours.state_dict()["param_groups"]] == [183, 0]
+
+
+def test_two_optimizers_of_different_sizes_share_the_library_prototype():
+    """refid_optim_step's ctypes prototype is pointer-typed, not sized by the first optimizer's tensor count."""
+    import inspect
+    from refid_b200 import optim
+    src = inspect.getsource(optim._ClipAdamBase.step)
+    assert "ctypes.c_long * n," not in src and "ctypes.cast" in src
+
+
 def test_metrics_and_event_util_need_cuda():
     from refid_b200 import event_util, metrics
     with pytest.raises(RuntimeError, match="no CPU path"):

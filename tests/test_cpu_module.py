@@ -123,3 +123,49 @@ def test_flat_gradient_all_reduce_two_ranks_gloo():
     [p.join(timeout=60) for p in procs]
     want = (torch.arange(8, dtype=torch.float32) * 1.5).tolist()
     assert res[0] == want and res[1] == want
+
+
+def _bcast_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from refid_b200.arch import FinalBidirectionAttenfusion
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(10 + rank)  # the reference seeds rank r with manual_seed + r (train.py:56): different initial weights
+    net = FinalBidirectionAttenfusion(img_chn=6, ev_chn=2, num_encoders=3, base_num_channels=32, num_block=1)
+    before = float(net.pred.conv2d.weight.double().sum())
+    net.grad_sync_group = dist.group.WORLD  # must broadcast rank 0's parameters, as DDP's constructor does
+    after = [float(p.double().sum()) for p in net.parameters()]
+    q.put((rank, before, after))
+    dist.destroy_process_group()
+
+
+def test_grad_sync_group_broadcasts_rank0_parameters_gloo():
+    """the no-DDP data-parallel path must start every replica from rank 0's weights."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = {r: (b, a) for r, b, a in (q.get(timeout=180) for _ in range(2))}
+    [p.join(timeout=60) for p in procs]
+    assert res[0][0] != res[1][0]      # the ranks really started from different weights
+    assert res[0][1] == res[1][1]      # ... and hold rank 0's afterwards
+    torch.manual_seed(10)
+    from refid_b200.arch import FinalBidirectionAttenfusion
+    ref = FinalBidirectionAttenfusion(img_chn=6, ev_chn=2, num_encoders=3, base_num_channels=32, num_block=1)
+    assert res[1][1] == [float(p.double().sum()) for p in ref.parameters()]
+
+
+def test_forward_only_plan_is_constant_in_T_and_options_exist():
+    from refid_b200 import engine
+    eng = engine.Engine(6, 2)
+    a, b = eng.workspace_bytes(1, 4, 256, 256, False), eng.workspace_bytes(1, 16, 256, 256, False)
+    # only the level-0 in-conv outputs (128 channels, all T) grow with T on a forward-only plan
+    per_step = 256 * 256 * 128 * 2
+    assert b - a <= 12 * per_step + (1 << 20), (a, b)
+    assert eng.workspace_bytes(1, 15, 720, 1280, False) < 8 << 30  # BASELINE.json configs[4] (r1: 50.8 GiB)
+    eng.set_option("graphs", 0)
+    eng.set_option("infer_fp16", 0)
+    with pytest.raises(RuntimeError, match="unknown option"):
+        eng.set_option("bogus", 1)
+    assert eng.graph_stats() == {"captures": 0, "replays": 0, "eager": 0, "failures": 0}
