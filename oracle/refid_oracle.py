@@ -283,14 +283,22 @@ def loss_and_grads(P: Dict[str, Tensor], x: Tensor, event: Tensor, gt: Tensor):
 # metrics restated for the PSNR parity check
 # ----------------------------------------------------------------------------------------------
 def tensor2img_uint8(t: Tensor):
-    """clamp[0,1] -> x255 -> round -> uint8 for a (3,H,W) tensor (basicsr/utils/img_util.py:90-117;
-    the RGB->BGR swap there does not change PSNR)."""
+    """clamp[0,1] -> x255 -> round (half to even, numpy) -> uint8 for a (3,H,W) tensor, channel order kept
+    (basicsr/utils/img_util.py:90-117; the RGB->BGR swap there permutes channels only).  Pinned by
+    tests/golden/psnr_cases.npz (generated from the unmodified reference function)."""
     return (t.detach().float().clamp(0, 1) * 255.0).round().to(torch.uint8)
 
 
-def psnr_uint8(a, b) -> float:
-    """calculate_psnr on uint8 images, float64 MSE (basicsr/metrics/psnr_ssim.py:47-61)."""
-    mse = ((a.double() - b.double()) ** 2).mean().item()
+def psnr_uint8(a, b, crop_border: int = 0) -> float:
+    """calculate_psnr on uint8 (C,H,W) images: float64 MSE inside the crop border, `inf` for identical images, and the
+    reference's peak rule `max_value = 1 if img1.max() <= 1 else 255` (basicsr/metrics/psnr_ssim.py:47-61).  Pinned by
+    tests/golden/psnr_cases.npz."""
+    a, b = a.double(), b.double()
+    if crop_border:
+        a = a[..., crop_border:-crop_border, crop_border:-crop_border]
+        b = b[..., crop_border:-crop_border, crop_border:-crop_border]
+    mse = ((a - b) ** 2).mean().item()
     if mse == 0:
         return float("inf")
-    return 20.0 * math.log10(255.0 / math.sqrt(mse))
+    max_value = 1.0 if a.max().item() <= 1 else 255.0
+    return 20.0 * math.log10(max_value / math.sqrt(mse))

@@ -1745,6 +1745,7 @@ int refid_create(const refid_cfg* cfg, refid_handle* out) {
   REFID_REQUIRE(cfg->out_chn >= 1 && cfg->out_chn <= 8, "refid_create: out_chn must be 1..8");
   Engine* e = new Engine();
   e->cfg = *cfg;
+  if (const char* g = getenv("REFID_GRAPHS")) e->opt_graphs = (g[0] == '0') ? 0 : 1;  // diagnostics (ncu launch lists)
   e->build_sites();
   *out = reinterpret_cast<refid_handle>(e);
   return 0;

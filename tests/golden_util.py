@@ -46,3 +46,16 @@ def check_grads(grads, gold, rtol_norm, atol_rel_samples):
         if err > atol_rel_samples * max(scale, 1e-12):
             bad.append((n, f"sample err {err:.3g} vs rms {scale:.3g}"))
     return bad
+
+
+def sample_error_ratios(grads, gold):
+    """name -> max |sampled gradient element - golden| / (golden tensor RMS), live parameters only."""
+    out = {}
+    for n in gold["names"]:
+        if n in gold["dead"] or gold["grad_norm"][n] <= 0:
+            continue
+        g = grads[n].detach().float().cpu()
+        idx = paramgen.grad_sample_index(n, g.numel())
+        scale = gold["grad_norm"][n] / max(g.numel(), 1) ** 0.5
+        out[n] = (g.flatten()[idx] - gold["grad_samples"][n]).abs().max().item() / max(scale, 1e-30)
+    return out

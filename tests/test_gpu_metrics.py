@@ -20,9 +20,7 @@ def test_psnr_frames_bit_identical_to_oracle(shape, crop):
     assert len(mine) == P.shape[0]
     for f in range(P.shape[0]):
         a, b = O.tensor2img_uint8(P[f]), O.tensor2img_uint8(G[f])
-        if crop:
-            a, b = a[:, crop:-crop, crop:-crop], b[:, crop:-crop, crop:-crop]
-        assert mine[f] == O.psnr_uint8(a, b), (f, mine[f], O.psnr_uint8(a, b))
+        assert mine[f] == O.psnr_uint8(a, b, crop), (f, mine[f], O.psnr_uint8(a, b, crop))
     assert metrics.psnr_frames(gt.cuda(), gt.cuda()) == [float("inf")] * P.shape[0]
 
 
@@ -40,3 +38,17 @@ def test_tensor2img_matches_oracle_layout():
         metrics.tensor2img(t)
     with pytest.raises(NotImplementedError):
         metrics.tensor2img(t.cuda(), out_type=np.float32)
+
+
+def test_gpu_metric_matches_reference_golden_vectors():
+    """The GPU kernel against vectors of the UNMODIFIED reference `tensor2img` / `calculate_psnr`
+    (tests/golden/make_psnr_golden.py): uint8 images bit-identical, PSNR to 1e-12 (crop border, ties, inf, max_value = 1)."""
+    import os
+    from refid_b200 import metrics
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "psnr_cases.npz"))
+    for n in sorted({k.split(".")[0] for k in z.files}):
+        p, q = torch.from_numpy(z[n + ".pred"]).cuda(), torch.from_numpy(z[n + ".gt"]).cuda()
+        assert np.array_equal(metrics.tensor2img(p), z[n + ".img_pred"]), n
+        assert np.array_equal(metrics.tensor2img(q), z[n + ".img_gt"]), n
+        want, got = float(z[n + ".psnr"]), metrics.psnr_frames(p, q, crop_border=int(z[n + ".crop"]))[0]
+        assert (np.isinf(want) and np.isinf(got)) or abs(want - got) < 1e-12, (n, want, got)

@@ -24,10 +24,15 @@ ic, ec, T, H, W = 6, 2, 2, 64, 64
 P = paramgen.make_params(O.param_shapes(ic, ec), seed=0)
 x, ev, gt = paramgen.make_inputs(world, T, H, W, ic, ec)
 def run(xs, evs, gts, group):
+    torch.manual_seed(100 + rank)  # as the reference's train.py:56: every rank constructs DIFFERENT initial weights
     net = FinalBidirectionAttenfusion(img_chn=ic, ev_chn=ec, num_encoders=3, base_num_channels=32, num_block=1)
-    net.load_state_dict(P, strict=True)
+    if rank == 0 or group is None:
+        net.load_state_dict(P, strict=True)  # only rank 0 holds the intended parameters ...
     net = net.cuda()
-    net.grad_sync_group = group
+    net.grad_sync_group = group  # ... the setter broadcasts them (DDP's constructor behaviour)
+    if group is not None:
+        for n, p in net.named_parameters():
+            assert torch.equal(p.detach().cpu(), P[n]), ("parameters were not broadcast from rank 0", n)
     out = net(x=xs.cuda(), event=evs.cuda())
     torch.sqrt((out - gts.cuda()) ** 2 + 1e-12).mean().backward()
     return {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
@@ -38,7 +43,7 @@ for n, g in full.items():
     d = (mine[n] - g).double().norm().item() / max(g.double().norm().item(), 1e-30)
     worst = max(worst, d)
 # identical up to bf16 rounding paths that depend on the batch geometry (tile order, atomics)
-assert worst < 5e-2, worst
+assert worst < 2e-2, worst
 t = torch.tensor([worst], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0: print("MULTI_OK", t.item())
 dist.destroy_process_group()

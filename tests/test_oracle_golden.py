@@ -68,3 +68,21 @@ def test_event_oracle_matches_reference_golden(case):
     assert out.dtype == np.float32 and out.shape == z["voxel"].shape
     assert np.array_equal(out, z["voxel"])
     assert np.array_equal(E.events_to_voxel_grid(ev, bins, w, h, "HWC"), z["voxel"].transpose(1, 2, 0))
+
+
+def test_metric_oracle_matches_reference_tensor2img_and_calculate_psnr():
+    """The restated validation metric against vectors of the unmodified reference functions
+    (tests/golden/make_psnr_golden.py): uint8 images bit-identical (up to the RGB->BGR channel swap), PSNR to 1e-12,
+    including the crop border, round-half-to-even ties, `inf`, and the max_value = 1 rule."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "psnr_cases.npz"))
+    names = sorted({k.split(".")[0] for k in z.files})
+    assert len(names) == 6
+    for n in names:
+        p, q = torch.from_numpy(z[n + ".pred"]), torch.from_numpy(z[n + ".gt"])
+        ip, iq = O.tensor2img_uint8(p), O.tensor2img_uint8(q)
+        assert np.array_equal(ip.flip(0).permute(1, 2, 0).numpy(), z[n + ".img_pred"]), n  # (H,W,C) BGR in the reference
+        assert np.array_equal(iq.flip(0).permute(1, 2, 0).numpy(), z[n + ".img_gt"]), n
+        want, got = float(z[n + ".psnr"]), O.psnr_uint8(ip, iq, int(z[n + ".crop"]))
+        assert (np.isinf(want) and np.isinf(got)) or abs(want - got) < 1e-12, (n, want, got)

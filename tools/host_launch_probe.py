@@ -33,5 +33,7 @@ for _ in range(5):
     host.append((time.perf_counter() - t0) * 1e3)
     torch.cuda.synchronize()
     dev.append(e0.elapsed_time(e1))
+st = next(s for k, s in net._states.items() if k[4])
+print("cuda graphs:", st["engine"].graph_stats())
 print(f"B={B} T={T} {H}x{W}: host enqueue {sorted(host)[2]:.1f} ms per step, device {sorted(dev)[2]:.1f} ms per step "
       f"({os.cpu_count()} host CPUs)")

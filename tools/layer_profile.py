@@ -42,6 +42,6 @@ for r in csv.DictReader(open(path)):
     agg[k][2] += float(r["gflop"])
 tot = sum(v[1] for v in agg.values())
 print(f"total device time (event-bracketed launches) {tot:.2f} ms for B={B} T={T} {H}x{W}")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     tf = v[2] / v[1] if v[1] > 0 else 0.0
     print(f"{v[1]:9.3f} ms {100 * v[1] / tot:5.1f}%  n={v[0]:4d}  {v[1] / v[0] * 1e3:8.1f} us/launch  {tf:7.1f} TF/s  {k[0]} {k[1]}")
