@@ -141,6 +141,16 @@ int refid_quant_psnr(const float* pred, const float* gt, int frames, int C, int 
                      int reverse_channels, unsigned long long* ssd, unsigned int* max_pred, unsigned char* img_pred,
                      unsigned char* img_gt, void* stream);
 
+/* Full-frame validation tiling (replaces `grids` / `grids_voxel` / `grids_inverse`,
+ * basicsr/models/twoImage_event_recurrent_model.py:128-270, transposes :115-126).  idx: ncrops x {i, j, trans_idx} int32 on the
+ * device (placement computed by the caller as the reference does, :201-243); trans_idx 0..7 = rot90 x (k % 4) of the crop,
+ * W-flipped first when k >= 4.  crop: (planes,H,W) -> (ncrops,planes,cs,cs).  merge: (ncrops,planes,cs,cs) -> (planes,H,W),
+ * every pixel the mean of the crops covering it (accumulated in crop order, as the reference's loop does). */
+int refid_grids_crop(const float* src, int planes, int H, int W, const int* idx, int ncrops, int crop_size, float* dst,
+                     void* stream);
+int refid_grids_merge(const float* parts, int planes, int H, int W, const int* idx, int ncrops, int crop_size, float* dst,
+                      void* stream);
+
 /* Event -> voxel-grid rasterisation (replaces `events_to_voxel_grid`, basicsr/data/event_util.py:6-66).
  * events: n rows of float32 [timestamp, x, y, polarity] on the device (the reference's array layout), 16-byte aligned;
  * voxel: (num_bins,height,width) fp32, or (height,width,num_bins) with hwc != 0; scratch: num_bins*height*width*8 bytes.

@@ -15,6 +15,7 @@ from copy import deepcopy
 import torch
 
 from . import _lib
+from . import grids
 from . import losses as loss_module
 from . import optim
 from .plugin import define_network
@@ -73,6 +74,42 @@ class TwoImageEventRecurrentRestorationModel:
         self.log_dict = {"l_pix": l_pix.detach()}
         _lib.raise_if_aborted()  # a kernel that hit its bounded wait invalidates everything after it: fail loudly
         return l_pix.detach()
+
+    # ---- full-frame validation tiling (reference :128-270; gated by `val.grids` in nondist_validation, :405-411) ----
+    def grids(self):
+        """`lq` (1, ..., H, W) -> overlapping crops on dim 0 (reference `grids`, :201-243)."""
+        val = self.opt["val"]
+        h, w = self.lq.shape[-2:]
+        self.original_size = tuple(self.lq.shape)
+        self.idxes = grids.crop_positions(h, w, val["crop_size"], val.get("trans_num", 1), val.get("random_crop_num", 0))
+        self.origin_lq = self.lq
+        self.lq = grids.crop(self.lq, self.idxes, val["crop_size"])
+
+    def grids_voxel(self):
+        """`voxel` (1, T, C, H, W) -> the same crops as `grids()` (reference `grids_voxel`, :128-199; the reference draws
+        its random crops independently for lq and voxel -- here one placement list serves both)."""
+        self.original_size_voxel = tuple(self.voxel.shape)
+        self.origin_voxel = self.voxel
+        self.voxel = grids.crop(self.voxel, self.idxes, self.opt["val"]["crop_size"])
+
+    def grids_inverse(self):
+        """Network outputs of the crops -> one (1, T, out_chn, H, W) frame, overlap-averaged (reference :245-270)."""
+        h, w = self.original_size[-2:]
+        self.output = grids.merge(self.output, self.idxes, h, w)
+        self.lq = self.origin_lq
+        self.voxel = self.origin_voxel
+
+    def validate_frame(self, data):
+        """One frame of `nondist_validation` (:395-417): feed, tile if `val.grids`, test, merge."""
+        self.feed_data(data)
+        tiled = (self.opt.get("val") or {}).get("grids") is not None
+        if tiled:
+            self.grids()
+            self.grids_voxel()
+        self.test()
+        if tiled:
+            self.grids_inverse()
+        return self.output
 
     def test(self):
         self.net_g.eval()

@@ -86,3 +86,24 @@ def test_metric_oracle_matches_reference_tensor2img_and_calculate_psnr():
         assert np.array_equal(iq.flip(0).permute(1, 2, 0).numpy(), z[n + ".img_gt"]), n
         want, got = float(z[n + ".psnr"]), O.psnr_uint8(ip, iq, int(z[n + ".crop"]))
         assert (np.isinf(want) and np.isinf(got)) or abs(want - got) < 1e-12, (n, want, got)
+
+
+def test_grids_oracle_and_host_placement_match_reference_methods():
+    """Crop placement, the 8 orientations and the overlap average against vectors of the unmodified reference methods
+    (tests/golden/make_grids_golden.py), for the numpy oracle and for the product's host-side placement list."""
+    import os
+    import numpy as np
+    from oracle import grids_oracle as G
+    from refid_b200 import grids
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grids_cases.npz"))
+    names = sorted({k.split(".")[0] for k in z.files})
+    assert len(names) == 4
+    for n in names:
+        cs, tn = (int(v) for v in z[n + ".cfg"])
+        fr = z[n + ".frame"]
+        parts, idx = G.grids(fr, cs, tn)
+        assert np.array_equal(np.array(idx), z[n + ".idx"]), n
+        assert grids.crop_positions(fr.shape[-2], fr.shape[-1], cs, tn) == idx, n
+        assert np.array_equal(parts, z[n + ".parts"]), n
+        out = (parts * (1.0 + np.arange(parts.shape[0], dtype=np.float32).reshape(-1, 1, 1, 1) / 10.0)).astype(np.float32)
+        assert np.array_equal(G.grids_inverse(out, idx, fr.shape[-2], fr.shape[-1]), z[n + ".merged"]), n
