@@ -151,6 +151,13 @@ int refid_grids_crop(const float* src, int planes, int H, int W, const int* idx,
 int refid_grids_merge(const float* parts, int planes, int H, int W, const int* idx, int ncrops, int crop_size, float* dst,
                       void* stream);
 
+/* Training-sample assembly (second half; replaces the crop / augment / channel-packing steps of
+ * `__getitem__`, basicsr/data/image_npy_dataset.py:189-232 with basicsr/data/transforms.py:88-129,163-238):
+ * dst[p][y][x] = plane plane_table[p] (>= 0: plane of src_a, < 0: plane -1-v of src_b; both (planes,H,W) fp32) at the crop
+ * window (top,left,ph,pw), horizontally / vertically flipped, then transposed if rot90 (dst is (nplanes, pw, ph) then). */
+int refid_crop_flip_gather(const float* src_a, const float* src_b, int H, int W, const int* plane_table, int nplanes,
+                           int top, int left, int ph, int pw, int hflip, int vflip, int rot90, float* dst, void* stream);
+
 /* Event -> voxel-grid rasterisation (replaces `events_to_voxel_grid`, basicsr/data/event_util.py:6-66).
  * events: n rows of float32 [timestamp, x, y, polarity] on the device (the reference's array layout), 16-byte aligned;
  * voxel: (num_bins,height,width) fp32, or (height,width,num_bins) with hwc != 0; scratch: num_bins*height*width*8 bytes.

@@ -107,3 +107,25 @@ def test_grids_oracle_and_host_placement_match_reference_methods():
         assert np.array_equal(parts, z[n + ".parts"]), n
         out = (parts * (1.0 + np.arange(parts.shape[0], dtype=np.float32).reshape(-1, 1, 1, 1) / 10.0)).astype(np.float32)
         assert np.array_equal(G.grids_inverse(out, idx, fr.shape[-2], fr.shape[-1]), z[n + ".merged"]), n
+
+
+def test_sample_assembly_oracle_matches_reference_functions():
+    """Crop / flip / transpose / deblur-voxel packing / sliding windows against vectors built with the unmodified
+    reference `triple_random_crop`, `augment`, `img2tensor` (tests/golden/make_sample_golden.py); also the product's
+    replay of the reference's random draws (same `random` seed => same crop window and flags)."""
+    import os
+    import random
+    import numpy as np
+    from oracle import sample_oracle as S
+    from refid_b200 import sample_pack
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sample_pack_cases.npz"))
+    names = sorted({k.split(".")[0] for k in z.files})
+    assert len(names) == 5
+    for n in names:
+        m, nn, gs, seed, top, left, hf, vf, rt = (int(v) for v in z[n + ".cfg"])
+        gs = None if gs < 0 else gs
+        r = S.assemble(list(z[n + ".lqs"]), list(z[n + ".gts"]), z[n + ".voxel"], m, nn, gs, top, left, hf, vf, rt)
+        assert np.array_equal(r["lq"], z[n + ".lq"]) and np.array_equal(r["voxel"], z[n + ".vox"]) and np.array_equal(r["gt"], z[n + ".gt"]), n
+        random.seed(seed)
+        H, W = z[n + ".voxel"].shape[:2]
+        assert sample_pack.draw_crop_and_flips(H, W, gs) == (top, left, bool(hf), bool(vf), bool(rt)), n
