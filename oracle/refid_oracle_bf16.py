@@ -70,9 +70,14 @@ def egaca_step(P, p: str, xe: Tensor, xi: Tensor, g_i: Tensor) -> Tensor:
     pooled = ge_full.mean((2, 3), keepdim=True)
     s = F.relu(F.conv2d(pooled, P[p + ".se_1.1.weight"], P[p + ".se_1.1.bias"]))
     s = torch.sigmoid(F.conv2d(s, P[p + ".se_1.3.weight"], P[p + ".se_1.3.bias"]))
-    cs = q(torch.cat((g_i * s, g_e * s), 1))
+    # the gate is folded into conv3: each sample's weights are scaled by s on their K side and rounded to bf16; the gated
+    # tensor itself is never stored (engine.cu: egaca_step)
     beta = P[p + ".beta"].view(-1)
-    y = q(F.conv2d(cs, qw(P[p + ".conv3.weight"] * beta.view(-1, 1, 1, 1)), P[p + ".conv3.bias"] * beta) + xe + xi)
+    w3 = P[p + ".conv3.weight"] * beta.view(-1, 1, 1, 1)                      # (64,128,1,1)
+    ws = qw(w3.unsqueeze(0) * torch.cat((s, s), 1).view(s.shape[0], 1, -1, 1, 1))  # (B,64,128,1,1)
+    gcat = torch.cat((g_i.expand(g_e.shape[0], -1, -1, -1), g_e), 1)
+    y3 = torch.einsum("bok,bkhw->bohw", ws[:, :, :, 0, 0], gcat) + (P[p + ".conv3.bias"] * beta).view(1, -1, 1, 1)
+    y = q(y3 + xe + xi)
     w4, b4 = _fold_ln(P, p + ".conv4", p + ".norm2")
     g4 = q(F.gelu(F.conv2d(q(lnhat(y)), qw(w4), b4)))
     gamma = P[p + ".gamma"].view(-1)

@@ -245,17 +245,45 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, i
   return make_idesc_16(M, N, a_mn, b_mn, false);
 }
 
-// exact (erf) GELU and its derivative (reference: nn.GELU(), fusion_modules.py:271)
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// Exact (erf) GELU and its derivative (reference: nn.GELU(), fusion_modules.py:271) from ONE exponential and ONE reciprocal:
+//   Phi(-|x|) = 0.5 erfc(|x|/sqrt2) = 0.5 (a1 t + ... + a5 t^5) exp(-x^2/2),  t = 1 / (1 + p |x| / sqrt2)
+// (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 in erf, i.e. 7.5e-8 in Phi: below fp32 rounding of the products it enters),
+// and exp(-x^2/2) is also the density the derivative needs.  ~16 instructions incl. two MUFU ops (ex2, rcp.approx) against
+// ~45 for erff + __expf: the GELU 1x1 conv of EGACA and the depthwise kernel were bound by exactly these instructions
+// (r1: 46 TFLOP/s on conv4).  The tail is formed as 0.5*poly*E directly (no 1 - erf cancellation for negative x).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
-
-// gelu(x) and gelu'(x) from one erf evaluation
+__device__ __forceinline__ float gelu_tail_f(float x, float* dens) {  // returns Phi(-|x|); *dens = exp(-x^2/2)
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(ax, 0.3275911f * 0.70710678118654752f, 1.0f));
+  const float E = exp2f(x * x * (-0.5f * 1.4426950408889634f));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  *dens = E;
+  return p * t * E;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float E;
+  const float h = gelu_tail_f(x, &E);
+  return x * (x < 0.f ? h : 1.0f - h);
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float E;
+  const float h = gelu_tail_f(x, &E);
+  return fmaf(x * E, 0.3989422804014327f, x < 0.f ? h : 1.0f - h);
+}
+// gelu(x) and gelu'(x) from one evaluation
 __device__ __forceinline__ void gelu_both_f(float x, float* g, float* dg) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  float E;
+  const float h = gelu_tail_f(x, &E);
+  const float cdf = x < 0.f ? h : 1.0f - h;
   *g = x * cdf;
-  *dg = cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  *dg = fmaf(x * E, 0.3989422804014327f, cdf);
 }
 
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }

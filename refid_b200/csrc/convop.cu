@@ -91,6 +91,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   const bool up2 = d.kind == CK_UP2;              // ConvTranspose 2x2 s2: a 1x1 conv whose four N blocks are the output parities
   const bool scatter4 = down_dgrad || up2;        // four replicas of the output groups, scattered with stride 2
   if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad && !down_fwd && !up2) return 0;
+  if (d.w_img_rows) return 0;  // per-image weights: tap-GEMM engine (its weight tile is fetched per pixel tile anyway)
   if (scatter4 && ngroups != 1) return 0;
   if (down_fwd && (d.nsrc != 1 || d.src[0].C % 64 || (d.H & 1) || (d.W & 1) || 4 * (d.src[0].C / 64) > 16)) return 0;
   const int GH = down_fwd ? d.H / 2 : d.H, GW = down_fwd ? d.W / 2 : d.W;  // grid the pixel tiles run over
@@ -205,6 +206,13 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     for (int g = 0; g < ngroups; ++g)
       for (int c = 0; c < groups[g].channels; c += seg) {
         EpiDesc e = groups[g].epi;
+        // the two addends are interchangeable; the halo epilogue prefetches `pre` two groups ahead but loads `pre2` at use
+        // (~800 exposed cycles per group): a lone pending addend (the residual passthrough of every trunk conv1 /
+        // main.0 data-gradient) must ride in the prefetched slot
+        if (!e.pre && e.pre2) {
+          e.pre = e.pre2;
+          e.pre2 = nullptr;
+        }
         e.coff += c;
         e.osy = e.osx = scatter4 ? 2 : 1;
         e.ooy = scatter4 ? (q >> 1) : 0;
@@ -281,6 +289,8 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
   if (make_mat_map(&p.tmB, d.w, d.w_rows, d.w_cols, BK, BN)) return 1;
   p.wrows_per_tap = d.wrows_per_tap;
   p.w_row0 = d.w_row0;
+  p.w_img_rows = d.w_img_rows;
+  REFID_REQUIRE(!d.w_img_rows || p.TN == 1, "build_conv: per-image weights need one image per tile (%dx%d grid)", gh, gw);
 
   // N blocks
   int nb = 0;
@@ -322,6 +332,7 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
 static int try_build_halowgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
   const bool down = d.kind == CK_DOWN4;
   if (d.kind != CK_3X3 && !down) return 0;
+  if (d.out_img_stride) return 0;
   if (down && (d.nsrc != 1 || d.src[0].C % 64 || (d.H & 1) || (d.W & 1) || q.C == 32)) return 0;
   for (int s = 0; s < d.nsrc; ++s)
     if (d.src[s].nmod) return 0;
@@ -455,7 +466,19 @@ int build_wgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
   if (chunks > p.num_tiles) chunks = p.num_tiles;
   if (chunks < 1) chunks = 1;
   l->pixel_chunks = chunks;
+  if (d.out_img_stride) {
+    REFID_REQUIRE(p.TN == 1, "build_wgrad: per-image outputs need one image per tile (%dx%d grid)", gh, gw);
+    p.out_img_stride = d.out_img_stride;
+    p.img_chunks = (chunks + d.N - 1) / d.N;
+    if (p.img_chunks < 1) p.img_chunks = 1;
+  }
   return 0;
+}
+
+bool one_image_per_tile(int N, int H, int W) {
+  int tw, th, tn;
+  pick_tile(N, H, W, &tw, &th, &tn);
+  return tn == 1;
 }
 
 }  // namespace refid

@@ -46,7 +46,11 @@ struct ConvDesc {
   int wrows_per_tap;
   int w_row0;
   int f16;  // operands and outputs are fp16 (forward-only plans); 0: bf16
+  int w_img_rows;        // build_conv: image n uses weight rows n * w_img_rows + ... (tap-GEMM engine, one image per tile)
+  long out_img_stride;   // build_wgrad: per-image outputs, floats between consecutive images' matrices (0: one summed matrix)
 };
+// one image per 128-pixel tile for this grid?  (per-image weights / per-image weight gradients need it)
+bool one_image_per_tile(int N, int H, int W);
 
 // Build params once (tensor maps are encoded here), launch many times.
 struct TapGemmLaunch {

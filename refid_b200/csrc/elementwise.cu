@@ -30,10 +30,12 @@ __global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict_
   const int G = Kp / 8;
   const long total = (long)B * Tn * H * G * W;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % W);
-    long r = idx / W;
-    const int g = (int)(r % G);
-    r /= G;
+    // channel group fastest: consecutive threads write consecutive 16-byte chunks of one pixel row (the x-fastest order
+    // wrote 16 B at a 64-byte stride: 0.85 ms for the 870 MB of the event head's input, ~1 TB/s)
+    const int g = (int)(idx % G);
+    long r = idx / G;
+    const int x = (int)(r % W);
+    r /= W;
     const int y = (int)(r % H);
     const int n_out = (int)(r / H);
     const int t = t0 + n_out / B, b = n_out % B;  // time steps [t0, t0+Tn) of the T in the input; output image (t-t0)*B + b
@@ -481,7 +483,25 @@ __global__ void __launch_bounds__(64) k_se_fwd(const float* __restrict__ pool_pa
   __syncthreads();
   float acc = p.b2[c];
   for (int j = 0; j < 32; ++j) acc += p.w2[c * 32 + j] * z[j];
-  s[n * 64 + c] = 1.f / (1.f + __expf(-acc));
+  const float sig = 1.f / (1.f + __expf(-acc));
+  s[n * 64 + c] = sig;
+  // The gate folded into the consuming 1x1 conv (fusion_modules.py:312-317: x*se, x_e*se, then conv3 on their concat):
+  // conv3(cat(g_i*s, g_e*s)) = (W3 . diag(s,s)) cat(g_i, g_e), so this sample's conv3 weights are scaled on their K side
+  // here and the gated 128-channel tensor is never written.  w3: fp32 [k = 128][co = 64] (the flat gradient layout);
+  // wf: 16-bit [co][k] (forward operand), wd: [k][co] (data-gradient operand), both per sample.
+  if (p.w3) {
+    __syncthreads();
+    m[c] = sig;  // reuse: the gate of this sample
+    __syncthreads();
+    __nv_bfloat16* wf = p.wf + (size_t)n * 8192;
+    __nv_bfloat16* wd = p.wd ? p.wd + (size_t)n * 8192 : nullptr;
+    for (int k = 0; k < 128; ++k) {
+      const float v = p.w3[k * 64 + c] * m[k & 63];
+      const uint32_t b = cvt_pack_rt(v, 0.f, p.f16) & 0xFFFFu;
+      reinterpret_cast<unsigned short*>(wf)[c * 128 + k] = (unsigned short)b;
+      if (wd) reinterpret_cast<unsigned short*>(wd)[k * 64 + c] = (unsigned short)b;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, const float* __restrict__ s,
@@ -492,7 +512,21 @@ __global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, con
   __shared__ float gq[64], gz[32], m[64], z[32];
   const int n = blockIdx.x, c = threadIdx.x;
   const float sv = s[n * 64 + c];
-  gq[c] = gs[n * 64 + c] * sv * (1.f - sv);  // gradient at the pre-sigmoid logits
+  float gsv;
+  if (p.mwg) {
+    // gate folded into conv3: M = per-sample weight gradient of the scaled conv, [k = 128][co = 64]:
+    //   dL/ds[c] = sum_{k in {c, c+64}} sum_co W3[k][co] M[k][co]
+    const float* M = p.mwg + (size_t)n * 8192;
+    float a = 0.f;  // (dL/dW3 is formed once per direction after the sweep: k_gate_wgrad)
+    for (int co = 0; co < 64; ++co) {  // rows c and c + 64
+      const int co2 = (co + c) & 63;     // rotate: conflict-free / spread the L2 lines
+      a += p.w3[c * 64 + co2] * M[c * 64 + co2] + p.w3[(c + 64) * 64 + co2] * M[(c + 64) * 64 + co2];
+    }
+    gsv = a;
+  } else {
+    gsv = gs[n * 64 + c];
+  }
+  gq[c] = gsv * sv * (1.f - sv);  // gradient at the pre-sigmoid logits
   m[c] = save_mean[n * 64 + c];
   if (c < 32) z[c] = save_z[n * 32 + c];
   __syncthreads();
@@ -513,102 +547,18 @@ __global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, con
   gpool[n * 64 + c] = acc * inv_hw;
 }
 
-// ---------------------------------------------------------------------------------------------
-// channel gating
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads) k_gate_fwd(const __nv_bfloat16* __restrict__ gi, const __nv_bfloat16* __restrict__ ge,
-                                                         const float* __restrict__ s, __nv_bfloat16* __restrict__ cs, int N, long hw,
-                                                         int f16) {
+// dL/dW3[k][co] += sum_j M_j[k][co] * s_j[k % 64] over all (step, sample) pairs j of one direction: M [count][128][64],
+// s [count][64].  One launch per direction after the sweep's back-propagation.
+__global__ void __launch_bounds__(256) k_gate_wgrad(const float* __restrict__ M, const float* __restrict__ s, int count,
+                                                    float* __restrict__ gw3) {
   pdl_launch_dependents();
   pdl_wait();
-  const long nvec = (long)N * hw * 8;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const long pix = i >> 3;
-    const int grp = (int)(i & 7);
-    const int n = (int)(pix / hw);
-    const float* sc = s + (size_t)n * 64 + grp * 8;
-    float a[8], b[8];
-    load8_rt(gi + i * 8, a, f16);
-    load8_rt(ge + i * 8, b, f16);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float f = __ldg(sc + k);
-      a[k] *= f;
-      b[k] *= f;
-    }
-    store8_rt(cs + (size_t)pix * 128 + grp * 8, a, f16);
-    store8_rt(cs + (size_t)pix * 128 + 64 + grp * 8, b, f16);
-  }
-}
-
-constexpr int kGatePix = 512;  // pixels per block in the reduction (16 per thread)
-
-__global__ void __launch_bounds__(kEwThreads) k_gate_bwd_reduce(const __nv_bfloat16* __restrict__ gcs,
-                                                                const __nv_bfloat16* __restrict__ gi,
-                                                                const __nv_bfloat16* __restrict__ ge, float* gs, long hw) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float sred[64];
-  if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
-  __syncthreads();
-  const int n = blockIdx.y;
-  const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int j = 0; j < kGatePix / 32; ++j) {
-    const long p = (long)blockIdx.x * kGatePix + j * 32 + pl;
-    if (p >= hw) break;
-    const size_t pix = (size_t)n * hw + p;
-    float a[8], b[8], ga[8], gb[8];
-    load8(gi + pix * 64 + grp * 8, a);
-    load8(ge + pix * 64 + grp * 8, b);
-    load8(gcs + pix * 128 + grp * 8, ga);
-    load8(gcs + pix * 128 + 64 + grp * 8, gb);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] += a[k] * ga[k] + b[k] * gb[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
-    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
-  }
-  if ((threadIdx.x & 31) < 8) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&sred[grp * 8 + k], acc[k]);
-  }
-  __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(gs + (size_t)n * 64 + threadIdx.x, sred[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(kEwThreads) k_gate_bwd_apply(const __nv_bfloat16* __restrict__ gcs, const float* __restrict__ s,
-                                                               const float* __restrict__ gpool,
-                                                               const __nv_bfloat16* __restrict__ d_e, float* gi_f32,
-                                                               __nv_bfloat16* __restrict__ gz_de, int N, long hw) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const long nvec = (long)N * hw * 8;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
-    const long pix = i >> 3;
-    const int grp = (int)(i & 7);
-    const int n = (int)(pix / hw);
-    const float* sc = s + (size_t)n * 64 + grp * 8;
-    const float* gp = gpool + (size_t)n * 64 + grp * 8;
-    float ga[8], gb[8], d[8];
-    load8(gcs + (size_t)pix * 128 + grp * 8, ga);
-    load8(gcs + (size_t)pix * 128 + 64 + grp * 8, gb);
-    load8(d_e + i * 8, d);
-    float4* o = reinterpret_cast<float4*>(gi_f32 + i * 8);
-    float4 f0 = o[0], f1 = o[1];
-    float sk[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sk[k] = __ldg(sc + k);
-    f0.x += ga[0] * sk[0]; f0.y += ga[1] * sk[1]; f0.z += ga[2] * sk[2]; f0.w += ga[3] * sk[3];
-    f1.x += ga[4] * sk[4]; f1.y += ga[5] * sk[5]; f1.z += ga[6] * sk[6]; f1.w += ga[7] * sk[7];
-    o[0] = f0;
-    o[1] = f1;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) gb[k] = (gb[k] * sk[k] + __ldg(gp + k)) * d[k];  // d = saved gelu'(z)
-    store8(gz_de + i * 8, gb);
-  }
+  const int i = blockIdx.x * 256 + threadIdx.x;  // 0 .. 8191
+  const int k = (i >> 6) & 63;
+  const int j0 = blockIdx.y, dj = gridDim.y;
+  float acc = 0.f;
+  for (int j = j0; j < count; j += dj) acc += M[(size_t)j * 8192 + i] * __ldg(s + (size_t)j * 64 + k);
+  atomicAdd(gw3 + i, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -770,28 +720,10 @@ int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const
   return 0;
 }
 
-int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const float* s, __nv_bfloat16* cs, int N, long hw,
-                    cudaStream_t st, int f16) {
-  unsigned blocks = blocks_for((long)N * hw * 8, kEwThreads);
-  if (blocks > 148u * 16u) blocks = 148u * 16u;
-  REFID_CUDA_CHECK(launch_k(k_gate_fwd, dim3(blocks), dim3(kEwThreads), 0, st, gi, ge, s, cs, N, hw, f16));
-  REFID_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-int launch_gate_bwd_reduce(const __nv_bfloat16* gcs, const __nv_bfloat16* gi, const __nv_bfloat16* ge, float* gs, int N, long hw,
-                           cudaStream_t st) {
-  dim3 grid(blocks_for(hw, kGatePix), N);
-  REFID_CUDA_CHECK(launch_k(k_gate_bwd_reduce, dim3(grid), dim3(kEwThreads), 0, st, gcs, gi, ge, gs, hw));
-  REFID_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-int launch_gate_bwd_apply(const __nv_bfloat16* gcs, const float* s, const float* gpool, const __nv_bfloat16* d_e, float* gi_f32,
-                          __nv_bfloat16* gz_de, int N, long hw, cudaStream_t st) {
-  unsigned blocks = blocks_for((long)N * hw * 8, kEwThreads);
-  if (blocks > 148u * 16u) blocks = 148u * 16u;
-  REFID_CUDA_CHECK(launch_k(k_gate_bwd_apply, dim3(blocks), dim3(kEwThreads), 0, st, gcs, s, gpool, d_e, gi_f32, gz_de, N, hw));
+int launch_gate_wgrad(const float* M, const float* s, int count, float* gw3, cudaStream_t st) {
+  int gy = count < 8 ? count : 8;
+  if (gy < 1) gy = 1;
+  REFID_CUDA_CHECK(launch_k(k_gate_wgrad, dim3(32, gy), dim3(256), 0, st, M, s, count, gw3));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -1,7 +1,8 @@
 // Memory-bound kernels around the tap-GEMM engine: layout conversion of the network inputs / output gradient,
 // bias-gradient column sums, masked gradient accumulation, and the pieces of EGACA (event-guided adaptive channel
 // attention, reference basicsr/models/archs/fusion_modules.py:237-333) that are not 1x1 GEMMs: per-pixel LayerNorm,
-// depthwise 3x3 + GELU (+ global pooling), the squeeze-excite MLP and the channel gating.
+// depthwise 3x3 + GELU (+ global pooling) and the squeeze-excite MLP, which also folds the channel gate into the weights of
+// the 1x1 conv that consumes the gated features.
 // The forward kernels take `f16`: the 16-bit storage is fp16 instead of bf16 (forward-only plans).
 // All activations are NHWC bf16, 16-byte vectorised (8 channels per thread); statistics and parameters are fp32.
 #pragma once
@@ -62,6 +63,14 @@ struct SeParams {
   float* gb1;
   float* gw2;
   float* gb2;
+  // gate folded into conv3 (null: off): fp32 master weights [128][64]; per-sample scaled 16-bit copies written by the
+  // forward ([n][64][128] and, on training plans, [n][128][64]); backward: per-sample weight gradients M [n][128][64] in,
+  // conv3's weight gradient out
+  const float* w3;
+  __nv_bfloat16* wf;
+  __nv_bfloat16* wd;
+  int f16;
+  const float* mwg;
 };
 int launch_se_fwd(const float* pool_part, int parts, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
                   cudaStream_t st);
@@ -69,16 +78,8 @@ int launch_se_fwd(const float* pool_part, int parts, float inv_hw, SeParams p, f
 int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const float* save_z, float inv_hw, SeParams p,
                   float* gpool, int N, cudaStream_t st);
 
-// cs[pix][0:64] = gi*s[n], cs[pix][64:128] = ge*s[n]
-int launch_gate_fwd(const __nv_bfloat16* gi, const __nv_bfloat16* ge, const float* s, __nv_bfloat16* cs, int N, long hw,
-                    cudaStream_t st, int f16 = 0);
-// gs[n][c] += sum_pix gcs[:, c]*gi + gcs[:, 64+c]*ge
-int launch_gate_bwd_reduce(const __nv_bfloat16* gcs, const __nv_bfloat16* gi, const __nv_bfloat16* ge, float* gs, int N,
-                           long hw, cudaStream_t st);
-// gi_f32 += gcs[:, :64]*s ;  gz_de = (gcs[:, 64:]*s + gpool[n]) * d_e      (d_e = saved gelu'(z_e))
-int launch_gate_bwd_apply(const __nv_bfloat16* gcs, const float* s, const float* gpool, const __nv_bfloat16* d_e, float* gi_f32,
-                          __nv_bfloat16* gz_de, int N, long hw, cudaStream_t st);
-
+// conv3's weight gradient with the gate folded in: gw3[k][co] += sum_j M[j][k][co] * s[j][k % 64]
+int launch_gate_wgrad(const float* M, const float* s, int count, float* gw3, cudaStream_t st);
 // Weight repacking: fp32 [ntaps][R][Cc] (gradient layout) -> bf16, per-tap copy or transpose, taps gathered by tapmap.
 struct PackDesc {
   long src_off;  // floats

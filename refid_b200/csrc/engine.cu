@@ -1040,7 +1040,85 @@ struct Engine {
     return g;
   }
 
+  // Per-direction arrays of the folded gate (EGACA, fusion_modules.py:251-259,312-317): slot = step index of the sweep.
+  struct GateCtx {
+    long s_off = -1;    // fp32 [slots][N][64]      the gate s
+    long wf_off = -1;   // 16-bit [slots][N][64][128]  conv3's forward weights scaled by s on their K side
+    long wd_off = -1;   // 16-bit [slots][N][128][64]  the same, data-gradient layout (training plans)
+    long m_off = -1;    // fp32 [slots][N][128][64]  per-sample weight gradients of the scaled conv (training plans)
+    int slots = 0, used = 0;
+  };
+  GateCtx gate_ctx[2];
+
+  void gate_ctx_alloc(int dir, int N) {
+    GateCtx& g = gate_ctx[dir];
+    g = GateCtx();
+    g.slots = train ? T : 1;
+    g.s_off = act_alloc((size_t)g.slots * N * 64 * 4);
+    g.wf_off = act_alloc((size_t)g.slots * N * 8192 * 2);
+    if (train) {
+      g.wd_off = act_alloc((size_t)g.slots * N * 8192 * 2);
+      g.m_off = act_alloc((size_t)g.slots * N * 8192 * 4);
+    }
+  }
+
+  // Image n of a conv-shaped launch as its own ConvDesc / OutGroup set (tiny grids, where one 128-pixel tile spans
+  // several images and per-image weights / outputs cannot be addressed inside one launch).
+  static void slice_image(ConvDesc* d, OutGroup* g, int ng, int n, int OH, int OW) {
+    for (int k = 0; k < d->nsrc; ++k) d->src[k].ptr += (size_t)n * d->H * d->W * d->src[k].pitch;
+    d->N = 1;
+    for (int i = 0; i < ng; ++i) {
+      EpiDesc& e = g[i].epi;
+      const size_t off = (size_t)n * OH * OW * e.C;
+      if (e.out) e.out += off;
+      if (e.out2) e.out2 += off;
+      if (e.out_pre) e.out_pre += off;
+      if (e.out_f32) e.out_f32 += off;
+      if (e.post) e.post += off;
+      if (e.pre) e.pre += off;
+      if (e.pre2) e.pre2 += off;
+      if (e.sv) e.sv += off;
+      if (e.bias) e.bias += (size_t)n * e.bias_nstride;
+    }
+  }
+
+  // 1x1 conv whose weights differ per image (`w` = [N][rows_per_image][K] 16-bit): one tap-GEMM launch when every
+  // 128-pixel tile lies inside one image, else one launch per image.
+  int emit_per_image_conv(ConvDesc d, const OutGroup* groups, int ng, const __nv_bfloat16* w, int rows_per_image, int cls,
+                          double flops, const char* tag) {
+    if (dry) return 0;
+    d.w = w;
+    d.w_row0 = 0;
+    d.wrows_per_tap = rows_per_image;
+    if (one_image_per_tile(d.N, d.H, d.W)) {
+      d.w_rows = (long)d.N * rows_per_image;
+      d.w_img_rows = rows_per_image;
+      TapGemmLaunch l;
+      if (build_conv(d, groups, ng, &l)) return 1;
+      emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, cls, flops, tag);
+      return 0;
+    }
+    const int N = d.N;
+    for (int n = 0; n < N; ++n) {
+      ConvDesc dn = d;
+      OutGroup gn[2];
+      for (int i = 0; i < ng; ++i) gn[i] = groups[i];
+      slice_image(&dn, gn, ng, n, d.H, d.W);
+      dn.w = w + (size_t)n * rows_per_image * d.w_cols;
+      dn.w_rows = rows_per_image;
+      dn.w_img_rows = 0;
+      TapGemmLaunch l;
+      if (build_conv(dn, gn, ng, &l)) return 1;
+      emit([l](cudaStream_t st) mutable { return run_conv(l, st); }, cls, flops / N, tag);
+    }
+    return 0;
+  }
+
   // One EGACA evaluation for direction `dir`: event feature xe (per step), image feature branch g_i (hoisted).
+  // The squeeze-excite gate is folded into conv3 (the conv that consumes the gated features): the SE kernel scales this
+  // sample's conv3 weights by s on their K side, conv3 then reads g_i / g_e directly, and in the backward pass the gate's
+  // gradient comes out of a per-sample weight-gradient GEMM -- the gated tensor, its gradient and the two reduction passes
+  // over them do not exist (r1: gate_fwd + gate_bwd_reduce + gate_bwd_apply, ~0.3 GB of traffic per call).
   int egaca_step(int dir, int xe, int xi, int g_i, const std::string& nm) {
     const std::string a = std::string(dir ? "encoders_forward" : "encoders_backward") + ".1.atten_fuse";
     const Ten te = tens[xe];
@@ -1053,16 +1131,24 @@ struct Engine {
     c1.in[0] = n_e;
     const int a_e = conv(c1);
     if (a_e < 0) return -1;
-    // small fp32 state: gate, saved mean / hidden, and their gradients; per-block partial sums of the global pool
+    GateCtx& gc = gate_ctx[dir];
+    REFID_REQUIRE(gc.slots > 0 && gc.used < (train ? gc.slots : 1 << 30), "EGACA gate arrays not allocated");
+    const int slot = train ? gc.used : 0;
+    gc.used++;
+    // small fp32 state: saved mean / hidden, pooled gradient; per-block partial sums of the global pool
     const int parts = dw_pool_parts(te.H, te.W);
-    const long small = act_alloc((size_t)N * (64 * 5 + 32) * 4);
-    const long s_off = small + N * 64 * 4, mean_off = small + N * 128 * 4, gs_off = small + N * 192 * 4,
-               gpool_off = small + N * 256 * 4, z_off = small + N * 320 * 4;
+    const long small = act_alloc((size_t)N * (64 * 2 + 32) * 4);
+    const long mean_off = small, gpool_off = small + N * 64 * 4, z_off = small + N * 128 * 4;
+    const long s_off = gc.s_off + (long)slot * N * 64 * 4;
+    const long wf_off = gc.wf_off + (long)slot * N * 8192 * 2;
+    const long wd_off = train ? gc.wd_off + (long)slot * N * 8192 * 2 : -1;
+    const long m_off = train ? gc.m_off + (long)slot * N * 8192 * 4 : -1;
     const long pool_off = act_alloc((size_t)N * parts * 64 * 4);
     const int g_e = dw(a_e, site(a + ".conv2_e"), pool_off, nm + ".g_e");
-    const int s1 = site(a + ".se_1.1"), s2 = site(a + ".se_1.3");
-    if (s1 < 0 || s2 < 0) return -1;
+    const int s1 = site(a + ".se_1.1"), s2 = site(a + ".se_1.3"), s3 = site(a + ".conv3");
+    if (s1 < 0 || s2 < 0 || s3 < 0) return -1;
     SeParams sp;
+    memset(&sp, 0, sizeof(sp));
     sp.w1 = wmaster + sites[s1].w_off;
     sp.b1 = wmaster + sites[s1].b_off;
     sp.w2 = wmaster + sites[s2].w_off;
@@ -1071,54 +1157,129 @@ struct Engine {
     sp.gb1 = gflat ? gflat + sites[s1].b_off : nullptr;
     sp.gw2 = gflat ? gflat + sites[s2].w_off : nullptr;
     sp.gb2 = gflat ? gflat + sites[s2].b_off : nullptr;
+    sp.w3 = wmaster + sites[s3].w_off;  // [k = 128][co = 64] fp32 (beta folded in by the host)
+    sp.wf = P(wf_off);
+    sp.wd = train ? P(wd_off) : nullptr;
+    sp.f16 = f16;
     const float inv_hw = 1.f / (float)hw;
-    const int cs = new_tensor(N, te.H, te.W, 128, nm + ".cs");
     {
       float *pool = PF(pool_off), *sg = PF(s_off), *mean = PF(mean_off), *z = PF(z_off);
-      const __nv_bfloat16 *pgi = P(tens[g_i].off), *pge = P(tens[g_e].off);
-      __nv_bfloat16* pcs = P(tens[cs].off);
-      emit([pool, parts, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, parts, inv_hw, sp, sg, mean, z, N, st); }, LC_OTHER, 0.0, "se_fwd");
-      const int h16 = f16;
-      emit([pgi, pge, sg, pcs, N, hw, h16](cudaStream_t st) { return launch_gate_fwd(pgi, pge, sg, pcs, N, hw, st, h16); }, LC_OTHER, 0.0, "gate_fwd");
+      cur_label = a;
+      emit([pool, parts, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, parts, inv_hw, sp, sg, mean, z, N, st); }, LC_OTHER, 0.0, ":se_fwd");
+    }
+    // y = conv3(cat(g_i, g_e)) with this step's per-sample weights, + xe + xi (fusion_modules.py:317-321)
+    const int y = new_tensor(N, te.H, te.W, 64, nm + ".y");
+    {
+      ConvDesc d;
+      memset(&d, 0, sizeof(d));
+      d.kind = CK_1X1;
+      d.nsrc = 2;
+      d.src[0] = {P(tens[g_i].off), 64, tens[g_i].pitch};
+      d.src[1] = {P(tens[g_e].off), 64, tens[g_e].pitch};
+      d.N = N;
+      d.H = te.H;
+      d.W = te.W;
+      d.w_cols = 128;
+      d.f16 = f16;
+      OutGroup g;
+      memset(&g, 0, sizeof(g));
+      g.channels = 64;
+      g.epi.out = P(tens[y].off);
+      g.epi.C = 64;
+      g.epi.bias = wmaster + sites[s3].b_off;
+      g.epi.pre = P(tens[xe].off);
+      g.epi.pre2 = P(tens[xi].off);
+      cur_label = sites[s3].key;
+      if (emit_per_image_conv(d, &g, 1, P(wf_off), 64, LC_CONV_FWD, 2.0 * N * hw * 128 * 64, ":fwd")) return -1;
     }
     if (train) {
       Engine* self = this;
-      tape.push_back([self, cs, g_i, g_e, sp, inv_hw, N, hw, s_off, mean_off, z_off, gs_off, gpool_off]() {
-        const __nv_bfloat16* gcs = nullptr;
-        if (self->finalize(cs, &gcs)) return 1;
-        if (!gcs) return 0;
-        float *sg = self->PF(s_off), *mean = self->PF(mean_off), *z = self->PF(z_off), *gs = self->PF(gs_off),
-              *gpool = self->PF(gpool_off);
-        const __nv_bfloat16 *pgi = self->P(self->tens[g_i].off), *pge = self->P(self->tens[g_e].off);
-        const __nv_bfloat16* pde = self->P(self->tens[g_e].mask_off);
-        self->ensure_gbuf(g_e);
-        self->tens[g_e].gwritten = true;
-        __nv_bfloat16* gz_de = self->P(self->tens[g_e].goff);
-        float* gi_f32 = self->PF(self->tens[g_i].gfoff);
-        self->tens[g_i].gfwritten = true;
-        self->emit([gs, N](cudaStream_t st) {
-          REFID_CUDA_CHECK(cudaMemsetAsync(gs, 0, (size_t)N * 64 * 4, st));
+      tape.push_back([self, y, xe, xi, g_i, g_e, sp, inv_hw, N, hw, s3, s_off, mean_off, z_off, gpool_off, wd_off, m_off]() mutable {
+        const __nv_bfloat16* gz = nullptr;
+        if (self->finalize(y, &gz)) return 1;
+        if (!gz) return 0;
+        const Site& cs3 = self->sites[s3];
+        const Ten ty = self->tens[y];
+        self->cur_label = cs3.key;
+        self->emit_colsum(gz, (long)N * hw, 64, self->gflat + cs3.b_off);
+        float *sg = self->PF(s_off), *mean = self->PF(mean_off), *z = self->PF(z_off), *gpool = self->PF(gpool_off),
+              *M = self->PF(m_off);
+        // (1) per-sample weight gradient of the scaled conv: M[n][k][co] = sum_pix cat(g_i, g_e)[k] * gz[co]
+        self->emit([M, N](cudaStream_t st) {
+          REFID_CUDA_CHECK(cudaMemsetAsync(M, 0, (size_t)N * 8192 * 4, st));
           return 0;
         });
-        self->emit([gcs, pgi, pge, gs, N, hw](cudaStream_t st) { return launch_gate_bwd_reduce(gcs, pgi, pge, gs, N, hw, st); }, LC_OTHER, 0.0, "gate_bwd_reduce");
-        self->emit([gs, sg, mean, z, inv_hw, sp, gpool, N](cudaStream_t st) {
-          return launch_se_bwd(gs, sg, mean, z, inv_hw, sp, gpool, N, st);
-        }, LC_OTHER, 0.0, "se_bwd");
-        self->emit([gcs, sg, gpool, pde, gi_f32, gz_de, N, hw](cudaStream_t st) {
-          return launch_gate_bwd_apply(gcs, sg, gpool, pde, gi_f32, gz_de, N, hw, st);
-        }, LC_OTHER, 0.0, "gate_bwd_apply");
-        self->release_grad(cs);
+        if (!self->dry) {
+          ConvDesc d;
+          memset(&d, 0, sizeof(d));
+          d.kind = CK_1X1;
+          d.nsrc = 2;
+          d.src[0] = {self->P(self->tens[g_i].off), 64, self->tens[g_i].pitch};
+          d.src[1] = {self->P(self->tens[g_e].off), 64, self->tens[g_e].pitch};
+          d.N = N;
+          d.H = ty.H;
+          d.W = ty.W;
+          ActSrc q = {gz, 64, ty.pitch};
+          const double fl = 2.0 * N * hw * 128 * 64;
+          if (one_image_per_tile(N, ty.H, ty.W)) {
+            d.out_img_stride = 8192;
+            WgradLaunch wl;
+            if (build_wgrad(d, q, M, &wl)) return 1;
+            self->emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, fl, ":wgrad");
+          } else {
+            for (int n = 0; n < N; ++n) {
+              ConvDesc dn = d;
+              slice_image(&dn, nullptr, 0, n, ty.H, ty.W);
+              ActSrc qn = q;
+              qn.ptr += (size_t)n * hw * ty.pitch;
+              WgradLaunch wl;
+              if (build_wgrad(dn, qn, M + (size_t)n * 8192, &wl)) return 1;
+              self->emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, fl / N, ":wgrad");
+            }
+          }
+        }
+        // (2) gate gradient from M, squeeze-excite backward -> pooled gradient per sample and channel
+        SeParams sb = sp;
+        sb.mwg = M;
+        self->emit([sg, mean, z, inv_hw, sb, gpool, N](cudaStream_t st) {
+          return launch_se_bwd(nullptr, sg, mean, z, inv_hw, sb, gpool, N, st);
+        }, LC_OTHER, 0.0, ":se_bwd");
+        // (3) data gradient with the scaled weights: d g_i accumulates in fp32 over the steps (one tensor for all T), d z_e =
+        //     (W^T gz . s + pooled gradient) * gelu'(z_e) goes straight into the depthwise conv's gradient buffer
+        self->ensure_gbuf(g_e);
+        self->tens[g_e].gwritten = true;
+        self->tens[g_i].gfwritten = true;
+        if (!self->dry) {
+          ConvDesc d;
+          memset(&d, 0, sizeof(d));
+          d.kind = CK_1X1;
+          d.nsrc = 1;
+          d.src[0] = {gz, 64, ty.pitch};
+          d.N = N;
+          d.H = ty.H;
+          d.W = ty.W;
+          d.w_cols = 64;
+          OutGroup g[2];
+          memset(g, 0, sizeof(g));
+          g[0].channels = 64;
+          g[0].epi.out_f32 = self->PF(self->tens[g_i].gfoff);
+          g[0].epi.C = 64;
+          g[1].channels = 64;
+          g[1].epi.out = self->P(self->tens[g_e].goff);
+          g[1].epi.C = 64;
+          g[1].epi.bias = gpool;
+          g[1].epi.bias_nstride = 64;
+          g[1].epi.sv = self->P(self->tens[g_e].mask_off);
+          g[1].epi.act = ACT_MULT;
+          if (self->emit_per_image_conv(d, g, 2, self->P(wd_off), 128, LC_CONV_DGRAD, 2.0 * N * hw * 128 * 64, ":dgrad")) return 1;
+        }
+        self->cur_label = "";
+        self->add_pending(xe, self->tens[y].gidx, self->tens[y].goff);
+        self->add_pending(xi, self->tens[y].gidx, self->tens[y].goff);
+        self->release_grad(y);
         return 0;
       });
     }
-    ConvOp c3;
-    c3.kind = CK_1X1;
-    c3.site = site(a + ".conv3");
-    c3.in[0] = cs;
-    c3.res = xe;
-    c3.res2 = xi;
-    const int y = conv(c3, nm + ".y");
-    if (y < 0) return -1;
     const int n_y = ln(y);
     ConvOp c4;
     c4.kind = CK_1X1;
@@ -1134,6 +1295,21 @@ struct Engine {
     c5.in[1] = g4;
     c5.nin = 2;
     return conv(c5, nm + ".u");
+  }
+
+  // conv3's weight gradient of one direction: sum over the sweep's (step, sample) pairs of M * s (after the sweep's BPTT)
+  int emit_gate_wgrad(int dir) {
+    const GateCtx& gc = gate_ctx[dir];
+    if (!train || gc.used == 0) return 0;
+    const int s3 = site(std::string(dir ? "encoders_forward" : "encoders_backward") + ".1.atten_fuse.conv3");
+    if (s3 < 0) return 1;
+    const float *M = PF(gc.m_off), *sg = PF(gc.s_off);
+    float* gw3 = gflat + sites[s3].w_off;
+    const int count = gc.used * B;
+    cur_label = sites[s3].key;
+    emit([M, sg, count, gw3](cudaStream_t st) { return launch_gate_wgrad(M, sg, count, gw3, st); }, LC_OTHER, 0.0, ":wgrad_gate");
+    cur_label = "";
+    return 0;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -1302,6 +1478,8 @@ struct Engine {
       mark_f32acc(g_i[d]);
     }
     const char* dirs[2] = {"encoders_backward", "encoders_forward"};
+    gate_ctx_alloc(0, B);
+    gate_ctx_alloc(1, B);
     // ---- backward sweep t = T-1 .. 0 (XXNet_final_attenfusion_arch.py:172-181)
     // Recurrent states live in (T+1)-slot series: slot t = h_t, the spare slot is the zero initial state.
     auto state_series = [&](int Hh, int Ww, int C, int pad_slot, int* pad_tensor) {
@@ -1723,6 +1901,7 @@ struct Engine {
       for (int i = (int)tape.size() - 1; i >= 0; --i)
         if (tape[i]()) return 1;
       if (emit_batched_grads()) return 1;
+      if (emit_gate_wgrad(0) || emit_gate_wgrad(1)) return 1;
     }
     tape.clear();
     planned = !dry;

@@ -144,11 +144,17 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
     if (GELU && e.act == ACT_GELU) {
       // out = gelu(z); out_pre = gelu'(z) for the backward pass (chunk-wise: 8 temporaries)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float dg[8];
+      if (e.out_pre) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gelu_both_f(v[8 * k + i], &v[8 * k + i], &dg[i]);
-        if (e.out_pre) store8_rt(e.out_pre + off + 8 * k, dg, F16 ? 1 : 0);
+        for (int k = 0; k < 4; ++k) {
+          float dg[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gelu_both_f(v[8 * k + i], &v[8 * k + i], &dg[i]);
+          store8_rt(e.out_pre + off + 8 * k, dg, F16 ? 1 : 0);
+        }
+      } else {  // forward-only plans keep no derivative
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
       }
     } else {
       if (e.out_pre) store32<F16>(e.out_pre + off, v);

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             uint8_t* b_dst = a_dst + A_BYTES;
             const CUtensorMap* am = &p.tmA[p.parity_mode ? p.tap_map[tap] : src];
             tma_load_4d(a_dst, am, &full_bar[s], slab * BK, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n0);
-            tma_load_2d(b_dst, &p.tmB, &full_bar[s], kglob, p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
+            tma_load_2d(b_dst, &p.tmB, &full_bar[s], kglob, p.w_row0 + tap * p.wrows_per_tap + nblk * BN + n0 * p.w_img_rows);
           }
         }
       }
@@ -282,6 +282,7 @@ int launch_tapgemm(TapGemmParams& p, int BN, int BK, int n_blocks, cudaStream_t 
   REFID_REQUIRE(n_blocks >= 1 && n_blocks <= kMaxNBlocks, "tapgemm: bad n_blocks %d", n_blocks);
   REFID_REQUIRE(p.num_taps >= 1 && p.num_taps <= kMaxTaps, "tapgemm: bad num_taps %d", p.num_taps);
   REFID_REQUIRE(p.TW * p.TH * p.TN == 128, "tapgemm: tile %dx%dx%d != 128", p.TW, p.TH, p.TN);
+  REFID_REQUIRE(!p.w_img_rows || p.TN == 1, "tapgemm: per-image weights need one image per tile (TN=%d)", p.TN);
 #define INST(bn, bk) \
   if (BN == bn && BK == bk) return p.f16 ? launch_inst<bn, bk, true>(p, n_blocks, stream) : launch_inst<bn, bk, false>(p, n_blocks, stream);
   INST(32, 32) INST(64, 32) INST(128, 32) INST(256, 32)

@@ -59,6 +59,8 @@ struct TapGemmParams {
   int N, H, W;  // output-grid extent
   int num_stages;
   int f16;  // fp16 instead of bf16 storage (forward-only plans)
+  int w_img_rows;  // > 0: image n uses the weight rows [n * w_img_rows, ...) (per-sample weights: EGACA's gate folded into
+                   // conv3, fusion_modules.py:312-317); needs TN == 1
 };
 
 // Host: geometry helper -- picks TW x TH x TN = 128 for an (N,H,W) grid.

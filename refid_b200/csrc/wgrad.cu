@@ -28,8 +28,17 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   int my_mt = p.num_mtiles - mt0;
   if (my_mt > p.mt_per_cta) my_mt = p.mt_per_cta;
   const int nb = blockIdx.z;
+  // tile walk of this CTA: every gridDim.x-th tile of the launch, or (per-image outputs) every img_chunks-th tile of ONE image
+  int t_first = blockIdx.x, t_stride = gridDim.x, t_limit = p.num_tiles, t_base = 0, img = 0;
+  if (p.img_chunks) {
+    img = blockIdx.x / p.img_chunks;
+    t_first = blockIdx.x % p.img_chunks;
+    t_stride = p.img_chunks;
+    t_limit = p.tiles_x * p.tiles_y;
+    t_base = img * t_limit;
+  }
   int my_tiles = 0;
-  for (int pt = blockIdx.x; pt < p.num_tiles; pt += gridDim.x) ++my_tiles;
+  for (int k = t_first; k < t_limit; k += t_stride) ++my_tiles;
 
   uint32_t ncols = 32;
   while ((int)ncols < p.mt_per_cta * p.BNq) ncols <<= 1;
@@ -57,7 +66,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
     if (warp == 0) {
       // TMA producer: uniform loop, one elected lane issues
       RingPos ring;
-      for (int pt = blockIdx.x; pt < p.num_tiles; pt += gridDim.x) {
+      for (int k = t_first; k < t_limit; k += t_stride) {
+        const int pt = t_base + k;
         const int tx_i = pt % p.tiles_x;
         const int ty_i = (pt / p.tiles_x) % p.tiles_y;
         const int tn_i = pt / (p.tiles_x * p.tiles_y);
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
       for (int mt = 0; mt < my_mt; ++mt) {
         const int row = (mt0 + mt) * 128 + m;
         const bool valid = row < p.total_rows;
-        float* orow = p.out + (size_t)row * p.CQ + (size_t)nb * p.BNq;
+        float* orow = p.out + (size_t)img * p.out_img_stride + (size_t)row * p.CQ + (size_t)nb * p.BNq;
 #pragma unroll 1
         for (int c0 = 0; c0 < p.BNq; c0 += 16) {
           float v[16];
@@ -176,6 +186,12 @@ int launch_wgrad(WgradParams& p, int pixel_chunks, cudaStream_t stream) {
   }
   if (pixel_chunks > p.num_tiles) pixel_chunks = p.num_tiles;
   if (pixel_chunks < 1) pixel_chunks = 1;
+  if (p.img_chunks) {
+    REFID_REQUIRE(p.TN == 1 && p.src_nmod[0] == 0 && p.src_nmod[1] == 0, "wgrad: per-image outputs need one image per tile");
+    const int tpi = p.tiles_x * p.tiles_y;
+    if (p.img_chunks > tpi) p.img_chunks = tpi;
+    pixel_chunks = p.N * p.img_chunks;
+  }
   const int mt_groups = (p.num_mtiles + p.mt_per_cta - 1) / p.mt_per_cta;
   dim3 grid(pixel_chunks, mt_groups, p.CQ / p.BNq);
   REFID_CUDA_CHECK(launch_k(wgrad_kernel, dim3(grid), dim3(kWThreads), smem, stream, p));

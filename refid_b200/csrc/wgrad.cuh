@@ -27,6 +27,8 @@ struct WgradParams {
   int TW, TH, TN, tiles_x, tiles_y, num_tiles;
   int N, H, W;
   int num_stages;
+  int img_chunks;        // > 0: per-image outputs -- CTA x works on image x / img_chunks only (its tiles x % img_chunks,
+  long out_img_stride;   //      + img_chunks, ...) and accumulates into out + image * out_img_stride; needs TN == 1
 };
 
 int launch_wgrad(WgradParams& p, int pixel_chunks, cudaStream_t stream);

@@ -3,7 +3,7 @@
 tag=${1:-r02a}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv,noheader
-timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -n 5 gpurun_out/pytest_gpu_$tag.log
+timeout 1800 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_gpu_$tag.log 2>&1; tail -n 25 gpurun_out/pytest_gpu_$tag.log
 grep -h "max-abs\|dPSNR\|sampled-gradient\|MULTI_OK" gpurun_out/pytest_gpu_$tag.log | head -20
 timeout 300 python tools/host_launch_probe.py > gpurun_out/host_launch_$tag.txt 2>&1; tail -n 2 gpurun_out/host_launch_$tag.txt
 timeout 300 python tools/host_launch_probe.py 1 23 256 256 >> gpurun_out/host_launch_$tag.txt 2>&1; tail -n 2 gpurun_out/host_launch_$tag.txt
