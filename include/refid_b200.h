@@ -84,6 +84,7 @@ int refid_backward(refid_handle h, const float* grad_out, void* stream);
  * plan stores fp16, 0 = bf16. */
 int refid_set_option(refid_handle h, const char* name, long value);
 int refid_graph_stats(refid_handle h, long out[4]);
+const char* refid_graph_error(refid_handle h); /* why the last capture failed ("" if none did) */
 int refid_plan_storage(refid_handle h);
 
 /* Roofline accounting: re-runs forward (+ backward) of the current plan on the tensors of the last call with a CUDA

@@ -91,7 +91,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   const bool up2 = d.kind == CK_UP2;              // ConvTranspose 2x2 s2: a 1x1 conv whose four N blocks are the output parities
   const bool scatter4 = down_dgrad || up2;        // four replicas of the output groups, scattered with stride 2
   if (d.kind != CK_3X3 && d.kind != CK_1X1 && !down_dgrad && !down_fwd && !up2) return 0;
-  if (d.w_img_rows) return 0;  // per-image weights: tap-GEMM engine (its weight tile is fetched per pixel tile anyway)
+  if (d.w_img_rows && d.kind != CK_1X1) return 0;  // per-image weights: 1x1 only here (else the tap-GEMM engine)
   if (scatter4 && ngroups != 1) return 0;
   if (down_fwd && (d.nsrc != 1 || d.src[0].C % 64 || (d.H & 1) || (d.W & 1) || 4 * (d.src[0].C / 64) > 16)) return 0;
   const int GH = down_fwd ? d.H / 2 : d.H, GW = down_fwd ? d.W / 2 : d.W;  // grid the pixel tiles run over
@@ -124,6 +124,10 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   HaloConvParams& h = out->hp;
   memset(&h, 0, sizeof(h));
   h.f16 = d.f16;
+  h.w_img_rows = d.w_img_rows;
+  for (int g = 0; g < ngroups; ++g)
+    if (groups[g].epi.bias && groups[g].epi.bias_nstride) h.bias_images = d.N;
+  if (h.bias_images && (size_t)h.bias_images * total * 4 > 32 * 1024) return 0;  // per-sample bias table must fit shared memory
   h.num_taps = (d.kind == CK_1X1 || up2) ? 1 : 9;
   h.halo = (d.kind == CK_1X1 || up2) ? 0 : 1;
   h.pitch_px = h.halo ? 10 : 8;
@@ -469,7 +473,8 @@ int build_wgrad(const ConvDesc& d, ActSrc q, float* outp, WgradLaunch* l) {
   if (d.out_img_stride) {
     REFID_REQUIRE(p.TN == 1, "build_wgrad: per-image outputs need one image per tile (%dx%d grid)", gh, gw);
     p.out_img_stride = d.out_img_stride;
-    p.img_chunks = (chunks + d.N - 1) / d.N;
+    // ~one CTA per SM over all images: every CTA ends with one atomic per output element, so fewer, longer CTAs win
+    p.img_chunks = (148 + d.N * ctas_per_chunk - 1) / (d.N * ctas_per_chunk);
     if (p.img_chunks < 1) p.img_chunks = 1;
   }
   return 0;

@@ -27,28 +27,33 @@ __global__ void __launch_bounds__(kEwThreads) k_unroll5(const float* __restrict_
                                                         int T, int Cin, int H, int W, int Kp, int f16, int t0, int Tn) {
   pdl_launch_dependents();
   pdl_wait();
+  // (kx, c) of every unrolled channel k = kx*Cin + c, once per block (the per-element integer divisions made the r1 kernel
+  // instruction-bound: 0.8 ms for the event head's input); channel group fastest, so consecutive threads write consecutive
+  // 16-byte chunks of one pixel.  One block walks whole pixel rows: no 64-bit division in the loop.
+  __shared__ short2 kmap[320];
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) kmap[k] = make_short2((short)(k / Cin), (short)(k % Cin));
+  __syncthreads();
   const int G = Kp / 8;
-  const long total = (long)B * Tn * H * G * W;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    // channel group fastest: consecutive threads write consecutive 16-byte chunks of one pixel row (the x-fastest order
-    // wrote 16 B at a 64-byte stride: 0.85 ms for the 870 MB of the event head's input, ~1 TB/s)
-    const int g = (int)(idx % G);
-    long r = idx / G;
-    const int x = (int)(r % W);
-    r /= W;
-    const int y = (int)(r % H);
-    const int n_out = (int)(r / H);
+  const int per_row = W * G;
+  const long rows = (long)B * Tn * H;
+  const size_t plane = (size_t)H * W;
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = (int)(row % H);
+    const int n_out = (int)(row / H);
     const int t = t0 + n_out / B, b = n_out % B;  // time steps [t0, t0+Tn) of the T in the input; output image (t-t0)*B + b
-    const float* src = in + ((size_t)(b * T + t) * Cin) * H * W + (size_t)y * W;
-    float v[8];
+    const float* src = in + ((size_t)(b * T + t) * Cin) * plane + (size_t)y * W;
+    __nv_bfloat16* dst = out + (size_t)row * W * Kp;
+    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+      const int g = e % G, x = e / G;
+      float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = g * 8 + i;
-      const int kx = k / Cin, c = k - kx * Cin;
-      const int xx = x + kx - 2;
-      v[i] = (kx < 5 && xx >= 0 && xx < W) ? __ldg(src + (size_t)c * H * W + xx) : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const short2 kc = kmap[g * 8 + i];
+        const int xx = x + kc.x - 2;
+        v[i] = (kc.x < 5 && xx >= 0 && xx < W) ? __ldg(src + (size_t)kc.y * plane + xx) : 0.f;
+      }
+      store8_rt(dst + (size_t)x * Kp + g * 8, v, f16);
     }
-    store8_rt(out + (((size_t)n_out * H + y) * W + x) * Kp + g * 8, v, f16);
   }
 }
 
@@ -463,73 +468,98 @@ __global__ void __launch_bounds__(kEwThreads, 1) k_dw_bwd(const __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------
 // squeeze-excite MLP: one block of 64 threads per sample
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_se_fwd(const float* __restrict__ pool_part, int parts, float inv_hw, SeParams p, float* s,
-                                               float* save_mean, float* save_z) {
+__global__ void __launch_bounds__(256) k_se_fwd(const float* __restrict__ pool_part, int parts, float inv_hw, SeParams p, float* s,
+                                                float* save_mean, float* save_z) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float m[64], z[32];
-  const int n = blockIdx.x, c = threadIdx.x;
-  float sum = 0.f;  // fixed-order reduction of the depthwise kernel's per-block partial sums
-  for (int b = 0; b < parts; ++b) sum += pool_part[((size_t)n * parts + b) * 64 + c];
-  m[c] = sum * inv_hw;
-  save_mean[n * 64 + c] = m[c];
-  __syncthreads();
-  if (c < 32) {
-    float acc = p.b1[c];
-    for (int i = 0; i < 64; ++i) acc += p.w1[c * 64 + i] * m[i];
-    z[c] = fmaxf(acc, 0.f);
-    save_z[n * 32 + c] = z[c];
+  __shared__ float m[64], z[32], red[4][64];
+  const int n = blockIdx.x, c = threadIdx.x & 63, part = threadIdx.x >> 6;  // 4 threads per channel
+  {
+    // fixed-order reduction of the depthwise kernel's per-block partial sums (bit-reproducible): each of the 4 threads of
+    // a channel sums every 4th partial in order, the four results are added in order
+    float sum = 0.f;
+    for (int b = part; b < parts; b += 4) sum += pool_part[((size_t)n * parts + b) * 64 + c];
+    red[part][c] = sum;
   }
   __syncthreads();
-  float acc = p.b2[c];
-  for (int j = 0; j < 32; ++j) acc += p.w2[c * 32 + j] * z[j];
-  const float sig = 1.f / (1.f + __expf(-acc));
-  s[n * 64 + c] = sig;
+  if (part == 0) {
+    m[c] = (((red[0][c] + red[1][c]) + red[2][c]) + red[3][c]) * inv_hw;
+    save_mean[n * 64 + c] = m[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int j = threadIdx.x;
+    float acc = p.b1[j];
+    for (int i = 0; i < 64; ++i) acc += p.w1[j * 64 + i] * m[i];
+    z[j] = fmaxf(acc, 0.f);
+    save_z[n * 32 + j] = z[j];
+  }
+  __syncthreads();
+  if (part == 0) {
+    float acc = p.b2[c];
+    for (int j = 0; j < 32; ++j) acc += p.w2[c * 32 + j] * z[j];
+    const float sig = 1.f / (1.f + __expf(-acc));
+    s[n * 64 + c] = sig;
+    red[0][c] = sig;
+  }
   // The gate folded into the consuming 1x1 conv (fusion_modules.py:312-317: x*se, x_e*se, then conv3 on their concat):
   // conv3(cat(g_i*s, g_e*s)) = (W3 . diag(s,s)) cat(g_i, g_e), so this sample's conv3 weights are scaled on their K side
   // here and the gated 128-channel tensor is never written.  w3: fp32 [k = 128][co = 64] (the flat gradient layout);
   // wf: 16-bit [co][k] (forward operand), wd: [k][co] (data-gradient operand), both per sample.
   if (p.w3) {
     __syncthreads();
-    m[c] = sig;  // reuse: the gate of this sample
-    __syncthreads();
+    const float* gate = red[0];
     __nv_bfloat16* wf = p.wf + (size_t)n * 8192;
-    __nv_bfloat16* wd = p.wd ? p.wd + (size_t)n * 8192 : nullptr;
-    for (int k = 0; k < 128; ++k) {
-      const float v = p.w3[k * 64 + c] * m[k & 63];
-      const uint32_t b = cvt_pack_rt(v, 0.f, p.f16) & 0xFFFFu;
-      reinterpret_cast<unsigned short*>(wf)[c * 128 + k] = (unsigned short)b;
-      if (wd) reinterpret_cast<unsigned short*>(wd)[k * 64 + c] = (unsigned short)b;
+    // forward layout [co][k]: thread -> (co, 8 consecutive k): one 16-byte store; reads of w3 are strided by 64 floats (L2)
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      const int co = i >> 4, k0 = (i & 15) * 8;
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = p.w3[(k0 + q) * 64 + co] * gate[(k0 + q) & 63];
+      store8_rt(wf + co * 128 + k0, v, p.f16);
+    }
+    if (p.wd) {  // data-gradient layout [k][co]: same order as w3 -- coalesced both ways
+      __nv_bfloat16* wd = p.wd + (size_t)n * 8192;
+      for (int i = threadIdx.x; i < 1024; i += 256) {
+        const int k = i >> 3, c0 = (i & 7) * 8;
+        const float g = gate[k & 63];
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = p.w3[k * 64 + c0 + q] * g;
+        store8_rt(wd + k * 64 + c0, v, p.f16);
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, const float* __restrict__ s,
-                                               const float* __restrict__ save_mean, const float* __restrict__ save_z, float inv_hw,
-                                               SeParams p, float* gpool) {
+__global__ void __launch_bounds__(256) k_se_bwd(const float* __restrict__ gs, const float* __restrict__ s,
+                                                const float* __restrict__ save_mean, const float* __restrict__ save_z, float inv_hw,
+                                                SeParams p, float* gpool) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float gq[64], gz[32], m[64], z[32];
-  const int n = blockIdx.x, c = threadIdx.x;
-  const float sv = s[n * 64 + c];
-  float gsv;
+  __shared__ float gq[64], gz[32], m[64], z[32], red[4][64];
+  const int n = blockIdx.x, c = threadIdx.x & 63, part = threadIdx.x >> 6;
   if (p.mwg) {
     // gate folded into conv3: M = per-sample weight gradient of the scaled conv, [k = 128][co = 64]:
-    //   dL/ds[c] = sum_{k in {c, c+64}} sum_co W3[k][co] M[k][co]
+    //   dL/ds[c] = sum_{k in {c, c+64}} sum_co W3[k][co] M[k][co]      (dL/dW3 is formed once per direction: k_gate_wgrad)
+    // 4 threads per gate channel, 16 output channels each, rotated so that neighbouring threads hit different L2 sectors
     const float* M = p.mwg + (size_t)n * 8192;
-    float a = 0.f;  // (dL/dW3 is formed once per direction after the sweep: k_gate_wgrad)
-    for (int co = 0; co < 64; ++co) {  // rows c and c + 64
-      const int co2 = (co + c) & 63;     // rotate: conflict-free / spread the L2 lines
-      a += p.w3[c * 64 + co2] * M[c * 64 + co2] + p.w3[(c + 64) * 64 + co2] * M[(c + 64) * 64 + co2];
+    float a = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q) {
+      const int co = part * 16 + ((q + c) & 15);
+      a += p.w3[c * 64 + co] * M[c * 64 + co] + p.w3[(c + 64) * 64 + co] * M[(c + 64) * 64 + co];
     }
-    gsv = a;
-  } else {
-    gsv = gs[n * 64 + c];
+    red[part][c] = a;
   }
+  __syncthreads();
+  if (threadIdx.x >= 64) return;
+  const float sv = s[n * 64 + c];
+  const float gsv = p.mwg ? ((red[0][c] + red[1][c]) + red[2][c]) + red[3][c] : gs[n * 64 + c];
   gq[c] = gsv * sv * (1.f - sv);  // gradient at the pre-sigmoid logits
   m[c] = save_mean[n * 64 + c];
   if (c < 32) z[c] = save_z[n * 32 + c];
-  __syncthreads();
+  asm volatile("bar.sync 1, 64;" ::: "memory");
   atomicAdd(p.gb2 + c, gq[c]);
   for (int j = 0; j < 32; ++j) atomicAdd(p.gw2 + c * 32 + j, gq[c] * z[j]);
   if (c < 32) {
@@ -538,7 +568,7 @@ __global__ void __launch_bounds__(64) k_se_bwd(const float* __restrict__ gs, con
     gz[c] = z[c] > 0.f ? acc : 0.f;
     atomicAdd(p.gb1 + c, gz[c]);
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, 64;" ::: "memory");
   float acc = 0.f;
   for (int j = 0; j < 32; ++j) {
     acc += p.w1[j * 64 + c] * gz[j];
@@ -603,9 +633,9 @@ int launch_unroll5(const float* in, __nv_bfloat16* out, int B, int T, int Cin, i
   REFID_REQUIRE(Kp % 32 == 0 && Kp >= 5 * Cin, "unroll5: Kp=%d too small for Cin=%d", Kp, Cin);
   if (Tn < 0) Tn = T;
   REFID_REQUIRE(t0 >= 0 && t0 + Tn <= T, "unroll5: steps [%d,%d) outside T=%d", t0, t0 + Tn, T);
-  const long total = (long)B * Tn * H * W * (Kp / 8);
-  unsigned blocks = blocks_for(total, kEwThreads);
-  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  REFID_REQUIRE(Kp <= 320, "unroll5: Kp=%d exceeds the channel table", Kp);
+  long rows = (long)B * Tn * H;
+  unsigned blocks = rows > 148L * 16 ? 148u * 16u : (unsigned)rows;
   REFID_CUDA_CHECK(launch_k(k_unroll5, dim3(blocks), dim3(kEwThreads), 0, s, in, out, B, T, Cin, H, W, Kp, f16, t0, Tn));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -708,14 +738,14 @@ int launch_dw_bwd(const __nv_bfloat16* gd, const __nv_bfloat16* a, const float* 
 
 int launch_se_fwd(const float* pool_part, int parts, float inv_hw, SeParams p, float* s, float* save_mean, float* save_z, int N,
                   cudaStream_t st) {
-  REFID_CUDA_CHECK(launch_k(k_se_fwd, dim3(N), dim3(64), 0, st, pool_part, parts, inv_hw, p, s, save_mean, save_z));
+  REFID_CUDA_CHECK(launch_k(k_se_fwd, dim3(N), dim3(256), 0, st, pool_part, parts, inv_hw, p, s, save_mean, save_z));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int launch_se_bwd(const float* gs, const float* s, const float* save_mean, const float* save_z, float inv_hw, SeParams p,
                   float* gpool, int N, cudaStream_t st) {
-  REFID_CUDA_CHECK(launch_k(k_se_bwd, dim3(N), dim3(64), 0, st, gs, s, save_mean, save_z, inv_hw, p, gpool));
+  REFID_CUDA_CHECK(launch_k(k_se_bwd, dim3(N), dim3(256), 0, st, gs, s, save_mean, save_z, inv_hw, p, gpool));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -161,6 +161,8 @@ struct Engine {
   static constexpr int kGraphSlots = 4;
   GraphSlot fwd_graphs[kGraphSlots], bwd_graphs[kGraphSlots];
   unsigned long graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  std::string graph_error;
   long graph_captures = 0, graph_replays = 0, graph_eager = 0, graph_failures = 0;
 
   void drop_graphs() {
@@ -208,18 +210,28 @@ struct Engine {
       ++graph_eager;
       return run_eager(ls, zero_grads, st);
     }
-    // second sighting: capture, instantiate, launch
+    // second sighting: capture, instantiate, launch.  The capture runs on the engine's own stream: the caller's stream is
+    // usually PyTorch's current stream = the legacy default stream, which cannot be captured.  Capturing executes nothing,
+    // so no ordering between the two streams is involved; the instantiated graph is then launched on the caller's stream.
     hit->stamp = ++graph_clock;
     cudaGraph_t graph = nullptr;
-    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    cudaError_t ce = cudaSuccess;
+    if (!cap_stream) ce = cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal);
+    bool ok = ce == cudaSuccess;
     if (ok) {
-      const int rc = run_eager(ls, zero_grads, st);
-      const cudaError_t ee = cudaStreamEndCapture(st, &graph);
-      ok = rc == 0 && ee == cudaSuccess && graph != nullptr;
+      const int rc = run_eager(ls, zero_grads, cap_stream);
+      ce = cudaStreamEndCapture(cap_stream, &graph);
+      if (rc != 0) graph_error = std::string("launch failed during capture: ") + get_error();
+      ok = rc == 0 && ce == cudaSuccess && graph != nullptr;
     }
-    if (ok) ok = cudaGraphInstantiate(&hit->exec, graph, 0) == cudaSuccess;
+    if (ok) {
+      ce = cudaGraphInstantiate(&hit->exec, graph, 0);
+      ok = ce == cudaSuccess;
+    }
     if (graph) cudaGraphDestroy(graph);
-    if (!ok) {  // not capturable on this driver: keep working with plain launches (visible in refid_graph_stats)
+    if (!ok) {  // not capturable on this driver: keep working with plain launches (visible in refid_graph_stats / _error)
+      if (ce != cudaSuccess) graph_error = cudaGetErrorString(ce);
       cudaGetLastError();
       hit->exec = nullptr;
       opt_graphs = 0;
@@ -1935,6 +1947,7 @@ int refid_destroy(refid_handle h) {
   if (!e) return 0;
   if (e->packs_dev) cudaFree(e->packs_dev);
   e->drop_graphs();
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   delete e;
   return 0;
 }
@@ -1966,9 +1979,16 @@ size_t refid_wpack_bytes(refid_handle h) {
 }
 
 int refid_workspace_bytes(refid_handle h, int B, int T, int H, int W, int train, size_t* out) {
+  using namespace refid;
   Engine* e = reinterpret_cast<Engine*>(h);
-  if (e->plan(B, T, H, W, train, nullptr, nullptr, nullptr, true)) return 1;
-  *out = e->gbase + e->gtop + 4096;
+  REFID_REQUIRE(e && out, "refid_workspace_bytes: null argument");
+  // a dry plan on a scratch engine with the same configuration and options: the handle's own plan (if any) stays intact
+  Engine tmp;
+  tmp.cfg = e->cfg;
+  tmp.opt_infer_fp16 = e->opt_infer_fp16;
+  tmp.build_sites();
+  if (tmp.plan(B, T, H, W, train, nullptr, nullptr, nullptr, true)) return 1;
+  *out = tmp.gbase + tmp.gtop + 4096;
   return 0;
 }
 
@@ -2044,6 +2064,8 @@ int refid_graph_stats(refid_handle h, long out[4]) {
 }
 
 int refid_plan_storage(refid_handle h) { return reinterpret_cast<Engine*>(h)->f16; }
+
+const char* refid_graph_error(refid_handle h) { return reinterpret_cast<Engine*>(h)->graph_error.c_str(); }
 
 // Re-runs forward (+ backward) of the current plan on the last call's tensors with a CUDA event pair around every
 // launch and sums device time, launch count and algorithmic FLOPs per launch class

@@ -16,7 +16,7 @@ int haloconv_plan(HaloConvParams* p, int BN, int NM, int mode) {
   int total_slabs = 0;
   for (int i = 0; i < p->nsrc; ++i) total_slabs += p->src_slabs[i];
   // weights resident for the whole kernel when they fit next to >= 2 activation stages
-  if (p->n_blocks == 1 && mode != 2) {
+  if (p->n_blocks == 1 && mode != 2 && !p->w_img_rows) {  // (per-image weights are streamed per item)
     p->resident_b = 1;
     p->stages_b = 0;
     for (int sa = total_slabs >= 3 ? 3 : 2; sa >= 2; --sa) {

@@ -41,6 +41,8 @@ struct HaloConvParams {
   int resident_b;                 // weights stay in shared memory for the whole kernel (n_blocks == 1)
   int stages_a, stages_b;
   int f16;  // activations / packed weights are fp16 (forward-only plans) instead of bf16
+  int w_img_rows;   // > 0: image n reads weight rows n * w_img_rows + ... (per-sample weights; streamed-weight path)
+  int bias_images;  // > 0: the bias table holds one row per image (EpiDesc::bias_nstride), bias_images = N
 };
 
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);

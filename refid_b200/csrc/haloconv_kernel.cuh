@@ -256,9 +256,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
   }
   // set-up above overlaps the tail of the kernel before; from here on global memory is read
   pdl_wait();
-  for (int i = threadIdx.x; i < p.n_blocks * BN; i += kHaloThreads) {
-    const EpiDesc& e = p.epi[i >> p.epi_shift];
-    sbias[i] = e.bias ? __ldg(e.bias + e.coff + (i & (p.epi_seg - 1))) : 0.f;
+  const int bias_row = p.n_blocks * BN;  // floats per table row; one row per image when the bias is per sample
+  for (int i = threadIdx.x; i < bias_row * (p.bias_images ? p.bias_images : 1); i += kHaloThreads) {
+    const int img = i / bias_row, ch = i - img * bias_row;
+    const EpiDesc& e = p.epi[ch >> p.epi_shift];
+    sbias[i] = e.bias ? __ldg(e.bias + (size_t)img * e.bias_nstride + e.coff + (ch & (p.epi_seg - 1))) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -310,7 +312,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
               mbar_wait(&b_empty[sb], rb.ph ^ 1u, 0x710 + sb);
               if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[sb], B_TILE);
-                tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * KC, p.w_row0 + tap * p.wrows_per_tap + nblk * BN);
+                tma_load_2d(b_base + (size_t)sb * B_TILE, &p.tmB, &b_full[sb], ks * KC,
+                            p.w_row0 + tap * p.wrows_per_tap + nblk * BN + n * p.w_img_rows);
               }
               rb.advance(SB);
             }
@@ -537,7 +540,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           tmem_ld16(taddr + 16, v + 16);
           tmem_ld_wait();
           if (valid) {
-            epi_math32<GELU, INPUTS, F16>(*e, v, nullptr, off, cseg, n, y, x, f, sbias + nblk * BN + c0);
+            epi_math32<GELU, INPUTS, F16>(*e, v, nullptr, off, cseg, n, y, x, f,
+                                          sbias + (p.bias_images ? n * bias_row : 0) + nblk * BN + c0);
             if (e->out) store32<F16>(e->out + off, v);
             if (INPUTS && e->out2) store32_sum<F16>(e->out2 + off, v, f.c);
           }
@@ -587,7 +591,8 @@ inline size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
   for (int i = 0; i < p.nsrc; ++i) total_slabs += p.src_slabs[i];
   const size_t b_total = p.resident_b ? (size_t)(p.masked ? p.resident_tiles : total_slabs * p.num_taps) * BN * p.kc * 2
                                       : (size_t)p.stages_b * BN * p.kc * 2;
-  return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes + (size_t)p.n_blocks * BN * 4 + 1024;
+  return (size_t)p.stages_a * a_bytes + b_total + kHaloBarBytes +
+         (size_t)p.n_blocks * BN * 4 * (p.bias_images ? p.bias_images : 1) + 1024;
 }
 
 

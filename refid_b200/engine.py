@@ -45,6 +45,8 @@ def _bind(L):
     L.refid_set_option.argtypes = [c_void_p, ctypes.c_char_p, c_long]
     L.refid_graph_stats.argtypes = [c_void_p, ctypes.POINTER(c_long * 4)]
     L.refid_plan_storage.argtypes = [c_void_p]
+    L.refid_graph_error.argtypes = [c_void_p]
+    L.refid_graph_error.restype = ctypes.c_char_p
     L.refid_debug_tensor.argtypes = [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p)] + [ctypes.POINTER(c_int)] * 5
     L._refid_bound = True
     return L
@@ -83,7 +85,10 @@ class Engine:
     def graph_stats(self):
         a = (c_long * 4)()
         self.L.refid_graph_stats(self.h, ctypes.byref(a))
-        return {"captures": a[0], "replays": a[1], "eager": a[2], "failures": a[3]}
+        d = {"captures": a[0], "replays": a[1], "eager": a[2], "failures": a[3]}
+        if a[3]:
+            d["error"] = self.L.refid_graph_error(self.h).decode()
+        return d
 
     def storage(self):
         """16-bit storage type of the current plan's activations / packed weights."""

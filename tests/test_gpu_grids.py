@@ -22,7 +22,8 @@ def test_crop_and_merge_bit_exact_against_reference_vectors():
         idx = grids.crop_positions(fr.shape[-2], fr.shape[-1], cs, tn)
         parts = grids.crop(fr, idx, cs)
         assert np.array_equal(parts.cpu().numpy(), z[n + ".parts"]), n
-        out = parts * (1.0 + torch.arange(parts.shape[0], device="cuda").view(-1, 1, 1, 1) / 10.0)
+        # the golden run formed these weights on the CPU (a CUDA `tensor / 10.0` multiplies by the reciprocal: 1 ulp off)
+        out = parts * (1.0 + torch.arange(parts.shape[0]).view(-1, 1, 1, 1) / 10.0).cuda()
         merged = grids.merge(out, idx, fr.shape[-2], fr.shape[-1])
         assert np.array_equal(merged.cpu().numpy(), z[n + ".merged"]), n
 
