@@ -173,16 +173,15 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       if (i < e.nchw_C) o[i * plane] = v[i];
   }
   if (e.out_f32) {
-    float4* o = reinterpret_cast<float4*>(e.out_f32 + off);
+    // fp32 accumulation target: fire-and-forget vector reductions (the add happens in the L2; no load, no exposed latency --
+    // the read-modify-write version stalled ~1 us per 32-channel group).  Every element receives exactly ONE add per launch
+    // and launches are stream-ordered, so the result does not depend on any ordering.
+    float* o = e.out_f32 + off;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = o[i];
-      t.x += v[4 * i];
-      t.y += v[4 * i + 1];
-      t.z += v[4 * i + 2];
-      t.w += v[4 * i + 3];
-      o[i] = t;
-    }
+    for (int i = 0; i < 8; ++i)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                   "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                   : "memory");
   }
   (void)v2;
 }

@@ -1,8 +1,10 @@
 #!/bin/bash
+tag=${1:-r02}
+timeout 900 python -m pytest tests/test_gpu_network.py tests/test_gpu_kernels.py -q -x > gpurun_out/pytest_quick_$tag.log 2>&1; tail -n 3 gpurun_out/pytest_quick_$tag.log
 # Round-2 ncu session (one GPU): launch list of a training step + `--set full` captures of the kernels VERDICT r1 asked
 # for: the dominant halo conv (all 3x3 shapes), both weight-gradient kernels, the tap-GEMM (heads, per-sample conv3), the
 # GELU 1x1, the stride-2 `down` data-gradient, and the EGACA memory-bound kernels.  Graph replay off (plain launches).
-tag=${1:-r02}
+
 export REFID_GRAPHS=0
 mkdir -p gpurun_out
 STEP="python tools/profile_step.py 8 2 256 256"
