@@ -180,9 +180,16 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   int n_ein = 0;
   for (int g = 0; g < ngroups; ++g) {
     const EpiDesc& e = groups[g].epi;
-    n_ein += (e.pre ? 1 : 0) + (e.pre2 ? 1 : 0) + ((e.sv || e.post) ? 1 : 0);
+    n_ein += (e.pre ? 1 : 0) + (e.pre2 ? 1 : 0) + ((e.sv || e.post || e.sv_bits) ? 1 : 0);
   }
   h.epi_inputs = n_ein > 0;
+  static const int l2pf = getenv("REFID_EPI_L2PF") ? atoi(getenv("REFID_EPI_L2PF")) : 0;
+  h.epi_l2pf = l2pf;
+  static const int rmw = getenv("REFID_F32_RMW") ? atoi(getenv("REFID_F32_RMW")) : 0;
+  h.f32_rmw = rmw;
+  static const int nobits = getenv("REFID_NO_SIGNBITS") ? 1 : 0;  // diagnostic: 16-bit mask operands as in round 1
+  if (nobits)
+    for (int g = 0; g < ngroups; ++g) const_cast<OutGroup*>(groups)[g].epi.sv_bits = nullptr;
   // preference: resident weights (two pixel tiles per item, else one) before streamed weights -- re-streaming the
   // weights of a C=64 dual-source conv per 256-pixel item costs more than the smaller M (measured 111 vs 83 us MMA-side)
   const int nm_pref = (2 * 2 * BN <= 512 && GH > 16) ? 2 : 1;
@@ -217,6 +224,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
           e.pre = e.pre2;
           e.pre2 = nullptr;
         }
+        if (e.sv_bits) e.sv = nullptr;  // the sign bits replace the 16-bit mask operand on this engine
         e.coff += c;
         e.osy = e.osx = scatter4 ? 2 : 1;
         e.ooy = scatter4 ? (q >> 1) : 0;

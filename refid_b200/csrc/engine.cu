@@ -44,6 +44,8 @@ struct Ten {
   int act = ACT_NONE;
   float slope = 0.f;
   long mask_off = -1;  // byte offset of the tensor act'(.) is evaluated on (own data, or the saved pre-activation)
+  long bits_off = -1;  // byte offset of the activation sign bits (one word per pixel and 32 channels; see EpiDesc), -1: none
+  int bits_pitch = 0;  // words per pixel
   bool need_grad = true;
   bool f32acc = false;  // gradient accumulated in fp32 (many contributions over time), converted when finalized
   long gfoff = -1;
@@ -508,6 +510,7 @@ struct Engine {
     t.rel = ((long)n0 * t.H * t.W * t.pitch + c0) * 2;
     t.off += t.rel;
     if (t.mask_off >= 0) t.mask_off += t.rel;
+    if (t.bits_off >= 0) t.bits_off += ((long)n0 * t.H * t.W * t.bits_pitch + c0 / 32) * 4;
     t.N = N;
     t.C = C;
     t.parent = parent;
@@ -601,6 +604,8 @@ struct Engine {
     const __nv_bfloat16* pre = nullptr;   // existing contents (accumulate)
     const __nv_bfloat16* pre2 = nullptr;  // one pending passthrough addend
     const __nv_bfloat16* sv = nullptr;
+    const uint32_t* sv_bits = nullptr;  // sign-bit form of an LReLU / ReLU mask (preferred by the halo-conv epilogue)
+    int sv_bits_pitch = 0;
     int act = ACT_NONE;
     float slope = 0.f;
     float* dstf = nullptr;
@@ -663,6 +668,10 @@ struct Engine {
       t->sv = P(tens[id].mask_off);
       t->act = tens[id].act == ACT_GELU ? ACT_MULT : tens[id].act;
       t->slope = tens[id].slope;
+      if (tens[id].act == ACT_LRELU && tens[id].bits_off >= 0) {
+        t->sv_bits = reinterpret_cast<const uint32_t*>(ws + tens[id].bits_off);
+        t->sv_bits_pitch = tens[id].bits_pitch;
+      }
     }
     tens[id].gwritten = true;
     return 0;
@@ -755,6 +764,15 @@ struct Engine {
       if (op.act == ACT_GELU && train) tens[op.out].mask_off = act_alloc((size_t)tens[op.out].elems() * 2);
     }
     else if (op.out >= 0 && !name.empty()) named[name] = op.out;
+    // training plans: LeakyReLU / ReLU outputs also get their derivative mask as sign bits (1/16 of the tensor's bytes);
+    // the data-gradient epilogues that target the tensor read those instead of the tensor (allocated in dry plans too)
+    if (train && op.act == ACT_LRELU && op.out >= 0 && !op.nchw_out && tens[op.out].parent < 0 && tens[op.out].bits_off < 0 &&
+        cout % 32 == 0) {
+      const int bt = new_tensor(in0.N, oh, ow, cout / 16);  // cout / 32 words = cout / 16 16-bit elements per pixel
+      tens[bt].need_grad = false;
+      tens[op.out].bits_off = tens[bt].off;
+      tens[op.out].bits_pitch = cout / 32;
+    }
     if (op.post >= 0 && op.out2 < 0) op.out2 = new_tensor(in0.N, oh, ow, cout, name.empty() ? "" : name + "+");
     if (!dry) {
       cur_label = s.key;
@@ -800,6 +818,10 @@ struct Engine {
         e.out = P(o.off);
         e.C = o.pitch;
         if (op.act == ACT_GELU && o.mask_off >= 0) e.out_pre = P(o.mask_off);
+        if (op.act == ACT_LRELU && o.bits_off >= 0) {
+          e.out_bits = reinterpret_cast<uint32_t*>(ws + o.bits_off);
+          e.out_bits_pitch = o.bits_pitch;
+        }
       }
       e.bias = s.b_off >= 0 ? wmaster + s.b_off : nullptr;
       e.act = op.act;
@@ -812,6 +834,7 @@ struct Engine {
       }
       TapGemmLaunch l;
       if (build_conv(d, &g, 1, &l)) return -1;
+      if (!l.use_halo && !op.nchw_out) tens[op.out].bits_off = -1;  // only the halo-conv epilogue writes the sign bits
       if (op.nchw_out) {
         Engine* self = this;
         const long toff = op.nchw_toff;
@@ -923,6 +946,8 @@ struct Engine {
           g.epi.pre = t.pre;
           g.epi.pre2 = t.pre2;
           g.epi.sv = t.sv;
+          g.epi.sv_bits = t.sv_bits;
+          g.epi.sv_bits_pitch = t.sv_bits_pitch;
           g.epi.act = t.act;
           g.epi.slope = t.slope;
           g.epi.out_f32 = t.dstf;

@@ -43,6 +43,8 @@ struct HaloConvParams {
   int f16;  // activations / packed weights are fp16 (forward-only plans) instead of bf16
   int w_img_rows;   // > 0: image n reads weight rows n * w_img_rows + ... (per-sample weights; streamed-weight path)
   int bias_images;  // > 0: the bias table holds one row per image (EpiDesc::bias_nstride), bias_images = N
+  int epi_l2pf;     // epilogue warps L2-prefetch the next item's global operands
+  int f32_rmw;      // diagnostic: fp32 accumulation targets by read-modify-write instead of vector reductions
 };
 
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);

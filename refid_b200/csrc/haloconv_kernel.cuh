@@ -30,10 +30,12 @@ constexpr int kHaloMaxStages = 8;
 // accumulator-ready wait -- instead of load -> ~800-cycle stall -> use in every 16-channel step.
 struct EpiPF {
   uint4 a[4], c[4];  // pre, (sv | post): 32 channels of this thread's pixel each (pre2 is rare and loaded at use)
+  uint32_t m;        // activation sign bits of the 32 channels (sv_bits)
 };
 
-__device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, bool valid, EpiPF& f) {
+__device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, size_t pix, int cword, bool valid, EpiPF& f) {
   if (!valid) return;
+  if (e.sv_bits) f.m = __ldg(e.sv_bits + pix * (size_t)e.sv_bits_pitch + cword);
   if (e.pre) {
     ldg256(e.pre + off, f.a[0], f.a[1]);
     ldg256(e.pre + off + 16, f.a[2], f.a[3]);
@@ -106,7 +108,7 @@ __device__ __forceinline__ void store32(__nv_bfloat16* ptr, const float* v) {
 // GELU (exact erf: ~60 instructions per element, twice) is compiled only into the GELU instantiations.
 template <bool GELU, bool INPUTS, bool F16>
 __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2, size_t off, int cseg, int n, int y, int x,
-                                           const EpiPF& f, const float* sbias) {
+                                           const EpiPF& f, const float* sbias, uint32_t* bits_dst, bool f32_rmw) {
   if (e.bias) {  // bias table of the launch in shared memory (with ~227 KB of smem in use the L1 is too small to cache it)
     const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
@@ -126,7 +128,12 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
 #pragma unroll
     for (int k = 0; k < 4; ++k) add_chunk8<F16>(v + 8 * k, r[k]);
   }
-  if (INPUTS && e.sv) {
+  if (INPUTS && e.sv_bits) {
+    const float sl = e.slope;
+    const uint32_t m = f.m;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= ((m >> i) & 1u) ? 1.f : sl;
+  } else if (INPUTS && e.sv) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -160,6 +167,12 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       if (e.out_pre) store32<F16>(e.out_pre + off, v);
       if (e.act == ACT_LRELU) {
         const float sl = e.slope;
+        if (bits_dst) {  // training plans: the derivative mask as sign bits (see EpiDesc)
+          uint32_t m = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f ? 1u : 0u) << i;
+          *bits_dst = m;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
       }
@@ -177,11 +190,21 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
     // the read-modify-write version stalled ~1 us per 32-channel group).  Every element receives exactly ONE add per launch
     // and launches are stream-ordered, so the result does not depend on any ordering.
     float* o = e.out_f32 + off;
+    if (f32_rmw) {  // diagnostic (REFID_F32_RMW=1): the round-1 read-modify-write
+      float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
-                   "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
-                   : "memory");
+      for (int i = 0; i < 8; ++i) {
+        float4 t = o4[i];
+        t.x += v[4 * i]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
+        o4[i] = t;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                     "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                     : "memory");
+    }
   }
   (void)v2;
 }
@@ -505,33 +528,34 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
         const int n = tile / tiles_per_img;
         const uint32_t buf = it & 1;
-        auto group_ctx = [&](int g, const EpiDesc*& e, size_t& off, int& cseg, int& y, bool& valid) {
+        auto group_ctx = [&](int g, const EpiDesc*& e, size_t& off, size_t& pix, int& cword, int& cseg, int& y, bool& valid) {
           const int j = g / GPT, c0 = (g % GPT) * 32;
           y = y0 + j * 16 + ty;
           valid = (y < p.H) && (x < p.W);
           const int ch = nblk * BN + c0;
           e = &p.epi[ch >> p.epi_shift];
           cseg = ch & epi_mask;
-          const size_t pix = ((size_t)n * e->OH + (size_t)(y * e->osy + e->ooy)) * e->OW + (size_t)(x * e->osx + e->oox);
+          pix = ((size_t)n * e->OH + (size_t)(y * e->osy + e->ooy)) * e->OW + (size_t)(x * e->osx + e->oox);
           off = pix * (size_t)e->C + e->coff + cseg;
+          cword = (e->coff + cseg) >> 5;
         };
         // 32-channel groups of this thread's pixel: TMEM -> registers -> arithmetic -> 256-bit global stores.  INPUTS
         // instantiations (residuals, masks, skip-sum operands) load group g+2's global operands while group g is
         // computed; the others carry neither the prefetch registers nor the second output.
         auto prefetch = [&](int g, EpiPF& f) {
           const EpiDesc* e;
-          size_t off;
-          int cseg, y;
+          size_t off, pix;
+          int cseg, y, cword;
           bool valid;
-          group_ctx(g, e, off, cseg, y, valid);
-          epi_prefetch32(*e, off, valid, f);
+          group_ctx(g, e, off, pix, cword, cseg, y, valid);
+          epi_prefetch32(*e, off, pix, cword, valid, f);
         };
         auto process = [&](int g, const EpiPF& f) {
           const EpiDesc* e;
-          size_t off;
-          int cseg, y;
+          size_t off, pix;
+          int cseg, y, cword;
           bool valid;
-          group_ctx(g, e, off, cseg, y, valid);
+          group_ctx(g, e, off, pix, cword, cseg, y, valid);
           const int j = g / GPT, c0 = (g % GPT) * 32;
           float v[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + (uint32_t)(j * BN + c0);
@@ -540,11 +564,39 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           tmem_ld_wait();
           if (valid) {
             epi_math32<GELU, INPUTS, F16>(*e, v, nullptr, off, cseg, n, y, x, f,
-                                          sbias + (p.bias_images ? n * bias_row : 0) + nblk * BN + c0);
+                                          sbias + (p.bias_images ? n * bias_row : 0) + nblk * BN + c0,
+                                          e->out_bits ? e->out_bits + pix * (size_t)e->out_bits_pitch + cword : nullptr,
+                                          p.f32_rmw != 0);
             if (e->out) store32<F16>(e->out + off, v);
             if (INPUTS && e->out2) store32_sum<F16>(e->out2 + off, v, f.c);
           }
         };
+        // L2 prefetch of the NEXT item's epilogue operands (residuals, masks, skip-sum addends): they are whole activation
+        // tensors streamed from HBM; the register prefetch below covers two groups (~1-2 k cycles), which under a loaded
+        // memory system is about one DRAM round trip -- with the lines already in L2 it covers the rest comfortably
+        if (INPUTS && p.epi_l2pf) {
+          const int item2 = item + (int)gridDim.x;
+          if (item2 < p.num_items) {
+            const int nblk2 = item2 % p.n_blocks, tile2 = item2 / p.n_blocks;
+            const int x2 = (tile2 % p.tiles_x) * 8 + tx;
+            const int y02 = ((tile2 / p.tiles_x) % p.tiles_y) * (16 * NM);
+            const int n2 = tile2 / tiles_per_img;
+#pragma unroll 1
+            for (int g = hsel; g < G; g += 2) {
+              const int j = g / GPT, c0 = (g % GPT) * 32;
+              const int y2 = y02 + j * 16 + ty;
+              if (y2 >= p.H || x2 >= p.W) continue;
+              const int ch = nblk2 * BN + c0;
+              const EpiDesc& e2 = p.epi[ch >> p.epi_shift];
+              const size_t pix = ((size_t)n2 * e2.OH + (size_t)(y2 * e2.osy + e2.ooy)) * e2.OW + (size_t)(x2 * e2.osx + e2.oox);
+              const size_t off2 = pix * (size_t)e2.C + e2.coff + (ch & epi_mask);
+              if (e2.pre) asm volatile("prefetch.global.L2 [%0];" ::"l"(e2.pre + off2));
+              const __nv_bfloat16* third = e2.sv ? e2.sv : e2.post;
+              if (third) asm volatile("prefetch.global.L2 [%0];" ::"l"(third + off2));
+              if (e2.pre2) asm volatile("prefetch.global.L2 [%0];" ::"l"(e2.pre2 + off2));
+            }
+          }
+        }
         EpiPF fa, fb;  // two register sets, alternating: no copies
         // the global operands do not depend on the accumulator: the first TWO groups are requested before the
         // accumulator-ready wait, every later group two groups ahead of its use

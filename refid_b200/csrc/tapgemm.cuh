@@ -21,6 +21,7 @@ enum ActKind : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_GELU = 2, ACT_MULT = 3 };
 
 // Epilogue of one N block (all pointers share pixel mapping, channel pitch C and channel offset coff).
 //   a = acc + bias[n*bias_nstride + c] + pre + pre2
+//   if sv_bits (halo engine): a *= bit ? 1 : slope
 //   if sv:  a *= act'(sv)      (LRELU: sv>0 ? 1 : slope, evaluated on the saved OUTPUT; MULT: a *= sv, sv = saved derivative)
 //   else :  if out_pre: out_pre = (act == GELU ? gelu'(a) : a);   a = act(a)
 //   out = a;  out_f32 += a;  out2 = a + post;  out_nchw[c < nchw_C] = a
@@ -42,6 +43,13 @@ struct EpiDesc {
   int osy, osx, ooy, oox, OH, OW;
   int act;
   float slope;
+  // Activation sign bits (halo-conv engine, training plans): one 32-bit word per pixel and 32-channel group, bit i = the
+  // pre-activation of channel 32*g + i is > 0.  A LeakyReLU / ReLU forward epilogue writes them (out_bits); the backward
+  // epilogue that targets the tensor reads them (sv_bits) INSTEAD of the 16-bit tensor itself: 1/16 of the bytes for the
+  // derivative mask, the most common epilogue operand of the data-gradient launches.
+  uint32_t* out_bits;
+  const uint32_t* sv_bits;
+  int out_bits_pitch, sv_bits_pitch;  // words per pixel
 };
 
 struct TapGemmParams {

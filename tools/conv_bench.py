@@ -7,20 +7,21 @@ import kernel_cases as K
 from refid_b200 import packing, _lib
 import ctypes
 
-def bench(cin, cout, H, W, N, cin2=0, pre=False, reps=20):
+def bench(cin, cout, H, W, N, cin2=0, pre=False, reps=20, sv=False):
     x = K.rb(K.g(N, cin + cin2, H, W, seed=1))
     w = K.rb(K.g(cout, cin + cin2, 3, 3, seed=2) / (3 * (cin + cin2) ** 0.5))
     b = K.g(cout, seed=3) * 0.1
     ins = [K.nhwc(x[:, :cin])] + ([K.nhwc(x[:, cin:])] if cin2 else [])
     wp = packing.pack_fwd(w).to(torch.bfloat16)
     r = K.nhwc(K.rb(K.g(N, cout, H, W, seed=4))) if pre else None
+    m = K.nhwc(K.rb(K.g(N, cout, H, W, seed=5))) if sv else None  # saved activation: the epilogue applies its LeakyReLU mask
     out = torch.empty(N, H, W, cout, device="cuda", dtype=torch.bfloat16)
     L = _lib.lib()
 
     def run():
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         rc = L.refid_test_conv(K.CK_3X3, 0, _lib.ptr(ins[0]), cin, _lib.ptr(ins[1] if cin2 else None), cin2, N, H, W, _lib.ptr(wp),
-                               ctypes.c_long(wp.shape[0]), wp.shape[1], cout, 0, cout, _lib.ptr(b), _lib.ptr(r), None, K.ACT_LRELU,
+                               ctypes.c_long(wp.shape[0]), wp.shape[1], cout, 0, cout, _lib.ptr(b), _lib.ptr(r), _lib.ptr(m), K.ACT_LRELU,
                                ctypes.c_float(0.1), _lib.ptr(out), None, None, None, None, st)
         _lib.check(rc, "conv")
 
@@ -50,11 +51,14 @@ def bench(cin, cout, H, W, N, cin2=0, pre=False, reps=20):
         rows = [buf[i * 8:i * 8 + 6] for i in range(148)]
         worst = max(rows, key=lambda r: r[0])
         print("   MMA warp cycles (slowest CTA): total %d, acc_empty wait %d, A wait %d, B wait %d, issue blocks %d, items %d" % tuple(worst))
-    print(f"cin {cin}+{cin2} cout {cout} {N}x{H}x{W} pre={pre}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF/s  (device time, CUDA-graph replay)", flush=True)
+    print(f"cin {cin}+{cin2} cout {cout} {N}x{H}x{W} pre={pre} sv={sv}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF/s  (device time, CUDA-graph replay)", flush=True)
 
-print("REFID_HALO_DBG =", os.environ.get("REFID_HALO_DBG"))
+print("REFID_EPI_L2PF =", os.environ.get("REFID_EPI_L2PF"))
 bench(64, 64, 256, 256, 8)
 bench(64, 64, 256, 256, 8, pre=True)
+bench(64, 64, 256, 256, 8, pre=True, sv=True)
+bench(128, 128, 128, 128, 8, pre=True)
+bench(128, 128, 128, 128, 8, pre=True, sv=True)
 bench(64, 64, 256, 256, 8, cin2=64)
 bench(128, 128, 128, 128, 8)
 bench(128, 128, 128, 128, 8, cin2=128)
