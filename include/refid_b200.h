@@ -74,6 +74,18 @@ int refid_forward(refid_handle h, const float* x, const float* event, float* out
  * Must follow a refid_forward on the same plan (train != 0). */
 int refid_backward(refid_handle h, const float* grad_out, void* stream);
 
+/* Parameter tensors <-> flat vector in one launch each way (replaces ~300 framework ops per training step).  Entry: `ptr` =
+ * the source tensor (gather) or the destination gradient tensor (scatter), device fp32, contiguous; n = taps*R*Cc floats at
+ * float offset flat_off.  mode 0: plain copy; mode 1: conv weight (Cc,R,taps) = PyTorch (Cout,Cin,kh,kw) <-> [tap][R][Cc].
+ * refid_flat_gather zero-fills `flat` first (alignment gaps, padded rows).  The table is host memory, read during the call. */
+typedef struct {
+  const void* ptr;
+  long flat_off;
+  int mode, taps, R, Cc;
+} refid_flat_entry;
+int refid_flat_gather(const refid_flat_entry* entries, int n, float* flat, long flat_floats, void* stream);
+int refid_flat_scatter(const refid_flat_entry* entries, int n, const float* gflat, void* stream);
+
 /* Engine options (name, value):
  *   "infer_fp16" (default 1; set before refid_plan): forward-only plans (train == 0) keep activations and packed weights
  *       as fp16 instead of bf16 -- same bytes and tensor-core rate, 11 instead of 8 significant bits, which brings the

@@ -116,6 +116,44 @@ def broadcast_parameters(module, group, src=0):
             off += t.numel()
 
 
+class _FlatParams(torch.autograd.Function):
+    """Parameter tensors -> flat vector (refid_flat_gather) with the inverse scatter as its backward."""
+
+    @staticmethod
+    def _table(ent, ptrs):
+        tab = (_engine.FlatEntry * len(ent))()
+        for i, ((off, mode, taps, R, Cc), p) in enumerate(zip(ent, ptrs)):
+            tab[i].ptr, tab[i].flat_off, tab[i].mode, tab[i].taps, tab[i].R, tab[i].Cc = p, off, mode, taps, R, Cc
+        return tab
+
+    @staticmethod
+    def forward(ctx, flat_floats, ent, *ins):
+        dev = ins[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("refid_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        srcs = [t.detach() if (t.is_contiguous() and t.dtype == torch.float32) else t.detach().float().contiguous() for t in ins]
+        flat = torch.empty(flat_floats, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _engine.flat_gather(_FlatParams._table(ent, [t.data_ptr() for t in srcs]), len(ent), flat)
+        ctx.ent, ctx.shapes, ctx.dev = ent, [tuple(t.shape) for t in ins], dev
+        return flat
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        sizes = [int(math.prod(s)) for s in ctx.shapes]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)  # 16-byte aligned pieces of one buffer
+        buf = torch.empty(offs[-1], dtype=torch.float32, device=ctx.dev)
+        base = buf.data_ptr()
+        with torch.cuda.device(ctx.dev):
+            _engine.flat_scatter(_FlatParams._table(ctx.ent, [base + 4 * o for o in offs[:-1]]), len(ctx.ent), g)
+        grads = [buf[o:o + n].view(s) if need else None
+                 for o, n, s, need in zip(offs[:-1], sizes, ctx.shapes, ctx.needs_input_grad[2:])]
+        return (None, None, *grads)
+
+
 class _RefidFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, event, flat, mod):
@@ -260,39 +298,56 @@ class FinalBidirectionAttenfusion(nn.Module):
                 return P[key + ".conv2d.weight"], P[key + ".conv2d.bias"]
         return P[key + ".weight"], P.get(key + ".bias")
 
-    def _flat(self, eng):
+    _FOLDED = ("head", "head_img", "enc0_in", "pred")
+
+    def _is_plain(self, key):
+        """The site's flat entry is a pure permutation of ONE parameter tensor (no fold, no stacking, no padding)."""
+        if key in self._FOLDED:
+            return False
+        if ".atten_fuse." in key:
+            return key.rsplit(".", 1)[1] in ("conv2", "conv2_e") or key.endswith((".se_1.1", ".se_1.3"))
+        return True
+
+    def _flat_inputs(self, eng):
+        """Host side of the flat parameter vector: the tensors the gather kernel reads and, per tensor, its table entry
+        (flat offset, mode, taps, R, Cc).  Plain sites hand their parameter tensors over as they are (the kernel applies
+        the (Cout,Cin,kh,kw) -> [tap][Cin][Cout] permutation, mode 1); the dozen folded / stacked / padded sites are first
+        brought into the flat layout by a few differentiable torch ops (mode 0)."""
         P = dict(self.named_parameters())
-        dev = P["pred.conv2d.weight"].device
-        pieces, pos = [], 0
-
-        def put(t, off):
-            nonlocal pos
-            if off > pos:
-                pieces.append(torch.zeros(off - pos, device=dev))
-            assert off >= pos, "engine parameter table is not monotone"
-            pieces.append(t.reshape(-1))
-            pos = off + t.numel()
-
+        ins, ent = [], []  # input tensors; (flat offset, mode, taps, R, Cc) per input
         for e in eng.entries:
-            w, b = self._effective(e["key"], P)
-            kind = e["kind"]
-            if kind == _engine.KIND_ROWS5:  # (32,Cin,5,5) -> [ky][kx*Cin + c][32], K zero-padded to R
-                g = w.permute(2, 3, 1, 0).reshape(5, 5 * w.shape[1], w.shape[0])
-                g = F.pad(g, (0, 0, 0, e["R"] - g.shape[1]))
-            elif kind == _engine.KIND_UP2:  # ConvTranspose2d (Cin,Cout,2,2) -> [a*2+b][Cout][Cin]
-                g = w.permute(2, 3, 1, 0).reshape(4, w.shape[1], w.shape[0])
-            elif kind == _engine.KIND_RAW:
-                g = w.reshape(e["R"], e["Cc"])
-            else:  # Conv2d (Cout,Cin,kh,kw) -> [ky*kw+kx][Cin][Cout]
-                g = w.permute(2, 3, 1, 0).reshape(e["taps"], w.shape[1], w.shape[0])
-            assert g.numel() == e["taps"] * e["R"] * e["Cc"], (e, tuple(w.shape))
-            put(g, e["w_off"])
+            key, kind = e["key"], e["kind"]
+            w, b = self._effective(key, P)
+            if self._is_plain(key) and kind != _engine.KIND_ROWS5:
+                if kind == _engine.KIND_RAW:
+                    ent.append((e["w_off"], 0, 1, e["R"], e["Cc"]))
+                else:  # Conv2d (Cout,Cin,kh,kw) / ConvTranspose2d (Cin,Cout,2,2): the kernel permutes
+                    assert tuple(w.shape[:2]) == (e["Cc"], e["R"]) and w.shape[2] * w.shape[3] == e["taps"], (e, tuple(w.shape))
+                    ent.append((e["w_off"], 1, e["taps"], e["R"], e["Cc"]))
+                assert w.numel() == e["taps"] * e["R"] * e["Cc"], (e, tuple(w.shape))
+                ins.append(w)
+            else:
+                if kind == _engine.KIND_ROWS5:  # (32,Cin,5,5) -> [ky][kx*Cin + c][32], K zero-padded to R
+                    g = w.permute(2, 3, 1, 0).reshape(5, 5 * w.shape[1], w.shape[0])
+                    g = F.pad(g, (0, 0, 0, e["R"] - g.shape[1]))
+                elif kind == _engine.KIND_RAW:
+                    g = w.reshape(e["R"], e["Cc"])
+                else:  # Conv2d (Cout,Cin,kh,kw) -> [ky*kw+kx][Cin][Cout]
+                    g = w.permute(2, 3, 1, 0).reshape(e["taps"], w.shape[1], w.shape[0])
+                assert g.numel() == e["taps"] * e["R"] * e["Cc"], (e, tuple(w.shape))
+                ins.append(g.contiguous())
+                ent.append((e["w_off"], 0, e["taps"], e["R"], e["Cc"]))
             if e["nbias"]:
                 assert b is not None and b.numel() == e["nbias"], e
-                put(b, e["b_off"])
-        if pos < eng.flat_floats:
-            pieces.append(torch.zeros(eng.flat_floats - pos, device=dev))
-        return torch.cat(pieces)
+                ins.append(b)
+                ent.append((e["b_off"], 0, 1, 1, e["nbias"]))
+        return ins, tuple(ent)
+
+    def _flat(self, eng):
+        """The engine's flat parameter vector as a differentiable function of the parameters: ONE gather kernel over the
+        table of `_flat_inputs` (refid_flat_gather); its backward is ONE scatter (refid_flat_scatter)."""
+        ins, ent = self._flat_inputs(eng)
+        return _FlatParams.apply(eng.flat_floats, ent, *ins)
 
     # ------------------------------------------------------------------------------------------
     # engine / plan cache

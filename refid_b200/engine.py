@@ -23,6 +23,22 @@ class _Entry(ctypes.Structure):
 KIND_CONV3, KIND_CONV1, KIND_DOWN4, KIND_UP2, KIND_ROWS5, KIND_RAW = range(6)
 
 
+class FlatEntry(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("flat_off", c_long), ("mode", c_int), ("taps", c_int), ("R", c_int), ("Cc", c_int)]
+
+
+def flat_gather(table, n, flat):
+    L = _bind(_lib.lib())
+    st = c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)
+    _lib.check(L.refid_flat_gather(table, n, _lib.ptr(flat), flat.numel(), st), "refid_flat_gather")
+
+
+def flat_scatter(table, n, gflat):
+    L = _bind(_lib.lib())
+    st = c_void_p(torch.cuda.current_stream(gflat.device).cuda_stream)
+    _lib.check(L.refid_flat_scatter(table, n, _lib.ptr(gflat), st), "refid_flat_scatter")
+
+
 def _bind(L):
     if getattr(L, "_refid_bound", False):
         return L
@@ -42,6 +58,8 @@ def _bind(L):
     L.refid_profile.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.refid_profile_csv.argtypes = [c_void_p, c_int, ctypes.c_char_p, c_void_p]
     L.refid_num_launches.argtypes = [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    L.refid_flat_gather.argtypes = [ctypes.POINTER(FlatEntry), c_int, c_void_p, c_long, c_void_p]
+    L.refid_flat_scatter.argtypes = [ctypes.POINTER(FlatEntry), c_int, c_void_p, c_void_p]
     L.refid_set_option.argtypes = [c_void_p, ctypes.c_char_p, c_long]
     L.refid_graph_stats.argtypes = [c_void_p, ctypes.POINTER(c_long * 4)]
     L.refid_plan_storage.argtypes = [c_void_p]

@@ -6,6 +6,7 @@ import re
 import pytest
 import torch
 
+import flat_util
 import paramgen
 from oracle import refid_oracle as O
 
@@ -52,7 +53,8 @@ def test_flat_vector_layout_and_folds():
     P = paramgen.make_params(O.param_shapes(6, 2))
     net.load_state_dict(P, strict=True)
     eng = net._table_engine()
-    flat = net._flat(eng)
+    ins, table = net._flat_inputs(eng)  # host logic; the gather itself is CUDA (refid_flat_gather, tested on the GPU)
+    flat = flat_util.assemble(eng.flat_floats, ins, table)
     assert flat.numel() == eng.flat_floats and flat.requires_grad
     ent = {e["key"]: e for e in eng.entries}
 

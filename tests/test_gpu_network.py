@@ -383,3 +383,26 @@ def test_highrev_crop_training_step():
         if r > 0 and abs(p.grad.double().norm().item() - r) > 0.08 * r:
             bad.append((n, p.grad.double().norm().item(), r))
     assert not bad, bad[:5]
+
+
+def test_flat_parameter_gather_and_scatter_kernels_are_exact():
+    """refid_flat_gather / refid_flat_scatter (parameter tensors <-> the engine's flat vector, one launch each way) against
+    the torch restatement of the rule (tests/flat_util.py): pure data movement, so bit-exact, forward and backward."""
+    import flat_util
+    from oracle import refid_oracle as O
+    ic, ec = 26, 2
+    P = paramgen.make_params(O.param_shapes(ic, ec), seed=3)
+    net = _net(ic, ec, P)
+    eng = net._table_engine()
+    flat = net._flat(eng)
+    ins, table = net._flat_inputs(eng)
+    want = flat_util.assemble(eng.flat_floats, ins, table)
+    assert flat.shape == want.shape and torch.equal(flat.detach(), want.detach())
+    g = torch.randn(eng.flat_floats, device="cuda")
+    mine = torch.autograd.grad(flat, list(net.parameters()), g, allow_unused=True)
+    ref = torch.autograd.grad(want, list(net.parameters()), g, allow_unused=True)
+    for (n, _), a, b in zip(net.named_parameters(), mine, ref):
+        assert (a is None) == (b is None), n
+        if a is not None:
+            assert torch.equal(a, b), n
+    _no_abort()
