@@ -3,10 +3,6 @@
 #include "haloconv_kernel.cuh"
 
 namespace refid {
-#ifdef REFID_HALO_TIMING
-__device__ long long g_halo_t[148 * 8];
-#endif
-
 int launch_haloconv_f16(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);  // haloconv_f16.cu
 
 

@@ -9,7 +9,7 @@
 
 namespace refid {
 #ifdef REFID_HALO_TIMING
-extern __device__ long long g_halo_t[148 * 8];
+static __device__ long long g_halo_t[148 * 8];  // one copy per translation unit; haloconv.cu (bf16) reports its own
 #define HT_DECL long long ht_acc = 0, ht_a = 0, ht_b = 0, ht_mma = 0, ht_t0 = clock64(), ht_x
 #define HT_BEGIN ht_x = clock64()
 #define HT_END(v) v += clock64() - ht_x
