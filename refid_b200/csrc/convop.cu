@@ -81,7 +81,7 @@ int fill_taps(int kind, int parity, TapTable* t) {
 
 // 4-D NHWC map whose box is the halo patch of one 8 x (16*NM) pixel tile: (64 channels, pitch_px, patch_rows, 1 image).
 static int make_patch_map(CUtensorMap* m, const ActSrc& s, int N, int H, int W, int pitch_px, int patch_rows, int kc) {
-  return make_act_map(m, s.ptr, N, H, W, s.pitch, s.C, 0, 0, 1, kc, pitch_px, patch_rows, 1);
+  return make_act_map(m, s.ptr, s.nmod ? s.nmod : N, H, W, s.pitch, s.C, 0, 0, 1, kc, pitch_px, patch_rows, 1);
 }
 
 // Returns 1 when the op was lowered onto the halo-conv engine, 0 when it does not qualify, -1 on error.
@@ -136,6 +136,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.nsrc = down_fwd ? 4 : d.nsrc;
   h.kc = kc;
   for (int s = 0; s < h.nsrc; ++s) h.src_slabs[s] = d.src[down_fwd ? 0 : s].C / kc;
+  for (int s = 0; s < d.nsrc && !down_fwd; ++s) h.src_nmod[s] = d.src[s].nmod;
   if (down_fwd) {
     // parity view q = (py,px) holds in[2i+py][2j+px]; input row 2Y+ky-1 = 2(Y+dy)+py  =>  py = 0 uses dy in {0,+1},
     // py = 1 uses dy in {-1,0} (same in x): 4 of the 9 taps per view, 16 (view, tap) pairs = the 16 kernel taps
@@ -255,6 +256,7 @@ int build_conv(const ConvDesc& d, const OutGroup* groups, int ngroups, TapGemmLa
   memset(&p, 0, sizeof(p));
   p.f16 = d.f16;
   REFID_REQUIRE(d.nsrc == 1 || (d.nsrc == 2 && !tt.parity_mode), "build_conv: dual source not allowed with parity views");
+  REFID_REQUIRE(!d.src[0].nmod && !d.src[1].nmod, "build_conv: a repeated source needs the halo-conv engine");
   REFID_REQUIRE(d.H % tt.grid_div == 0 && d.W % tt.grid_div == 0, "build_conv: H,W must be even for stride-2 ops");
 
   int BK = 64;

@@ -25,7 +25,7 @@ struct ActSrc {
   const __nv_bfloat16* ptr;
   int C;      // channels read (K extent of this source)
   int pitch;  // elements per pixel in memory
-  int nmod;   // weight-gradient only: this source has nmod images, image n of the launch reads image n % nmod (0: off)
+  int nmod;   // this source has nmod images, image n of the launch reads image n % nmod (0: off); halo-conv engine / wgrad
 };
 
 struct OutGroup {

@@ -92,6 +92,7 @@ struct ConvOp {
   long nchw_toff = 0, nchw_nstride = 0;
   bool no_tape = false;
   bool defer_in1 = false;  // in[1] is the same tensor at every step: its gradient is computed once from the summed dL/dZ
+  bool rep_in1 = false;    // in[1] has fewer images than in[0] and repeats along the image axis (chunk ops; implies defer_in1)
 };
 
 typedef std::function<int(cudaStream_t)> Launch;
@@ -783,7 +784,7 @@ struct Engine {
       int cin_total = 0;
       for (int k = 0; k < op.nin; ++k) {
         const Ten& t = tens[op.in[k]];
-        d.src[k] = {P(t.off), t.C, t.pitch};
+        d.src[k] = {P(t.off), t.C, t.pitch, (k == 1 && op.rep_in1) ? t.N : 0};
         cin_total += t.C;
       }
       d.N = in0.N;
@@ -912,7 +913,7 @@ struct Engine {
         d.nsrc = op.nin;
         for (int k = 0; k < op.nin; ++k) {
           const Ten& t = tens[op.in[k]];
-          d.src[k] = {P(t.off), t.C, t.pitch};
+          d.src[k] = {P(t.off), t.C, t.pitch, (k == 1 && op.rep_in1) ? t.N : 0};
         }
         d.N = in0.N;
         d.H = in0.H;
@@ -1083,7 +1084,8 @@ struct Engine {
     long wf_off = -1;   // 16-bit [slots][N][64][128]  conv3's forward weights scaled by s on their K side
     long wd_off = -1;   // 16-bit [slots][N][128][64]  the same, data-gradient layout (training plans)
     long m_off = -1;    // fp32 [slots][N][128][64]  per-sample weight gradients of the scaled conv (training plans)
-    int slots = 0, used = 0;
+    int slots = 0;
+    long cap = 0, used = 0;  // samples (= step x image pairs) the arrays hold / handed out so far
   };
   GateCtx gate_ctx[2];
 
@@ -1091,6 +1093,7 @@ struct Engine {
     GateCtx& g = gate_ctx[dir];
     g = GateCtx();
     g.slots = train ? T : 1;
+    g.cap = (long)g.slots * N;
     g.s_off = act_alloc((size_t)g.slots * N * 64 * 4);
     g.wf_off = act_alloc((size_t)g.slots * N * 8192 * 2);
     if (train) {
@@ -1156,7 +1159,7 @@ struct Engine {
   // sample's conv3 weights by s on their K side, conv3 then reads g_i / g_e directly, and in the backward pass the gate's
   // gradient comes out of a per-sample weight-gradient GEMM -- the gated tensor, its gradient and the two reduction passes
   // over them do not exist (r1: gate_fwd + gate_bwd_reduce + gate_bwd_apply, ~0.3 GB of traffic per call).
-  int egaca_step(int dir, int xe, int xi, int g_i, const std::string& nm) {
+  int egaca_step(int dir, int xe, int xi, int g_i, const std::string& nm, int u_preset = -1) {
     const std::string a = std::string(dir ? "encoders_forward" : "encoders_backward") + ".1.atten_fuse";
     const Ten te = tens[xe];
     const int N = te.N;
@@ -1169,17 +1172,19 @@ struct Engine {
     const int a_e = conv(c1);
     if (a_e < 0) return -1;
     GateCtx& gc = gate_ctx[dir];
-    REFID_REQUIRE(gc.slots > 0 && gc.used < (train ? gc.slots : 1 << 30), "EGACA gate arrays not allocated");
-    const int slot = train ? gc.used : 0;
-    gc.used++;
+    // training plans keep every (step, image) pair's gate arrays: this call's N images (one step, or a chunk of steps) take
+    // the next N sample slots; forward-only plans reuse slot 0
+    REFID_REQUIRE(gc.slots > 0 && (!train || gc.used + N <= gc.cap), "EGACA gate arrays not allocated / exhausted");
+    const long samp = train ? gc.used : 0;
+    if (train) gc.used += N;
     // small fp32 state: saved mean / hidden, pooled gradient; per-block partial sums of the global pool
     const int parts = dw_pool_parts(te.H, te.W);
     const long small = act_alloc((size_t)N * (64 * 2 + 32) * 4);
     const long mean_off = small, gpool_off = small + N * 64 * 4, z_off = small + N * 128 * 4;
-    const long s_off = gc.s_off + (long)slot * N * 64 * 4;
-    const long wf_off = gc.wf_off + (long)slot * N * 8192 * 2;
-    const long wd_off = train ? gc.wd_off + (long)slot * N * 8192 * 2 : -1;
-    const long m_off = train ? gc.m_off + (long)slot * N * 8192 * 4 : -1;
+    const long s_off = gc.s_off + samp * 64 * 4;
+    const long wf_off = gc.wf_off + samp * 8192 * 2;
+    const long wd_off = train ? gc.wd_off + samp * 8192 * 2 : -1;
+    const long m_off = train ? gc.m_off + samp * 8192 * 4 : -1;
     const long pool_off = act_alloc((size_t)N * parts * 64 * 4);
     const int g_e = dw(a_e, site(a + ".conv2_e"), pool_off, nm + ".g_e");
     const int s1 = site(a + ".se_1.1"), s2 = site(a + ".se_1.3"), s3 = site(a + ".conv3");
@@ -1285,7 +1290,9 @@ struct Engine {
         //     (W^T gz . s + pooled gradient) * gelu'(z_e) goes straight into the depthwise conv's gradient buffer
         self->ensure_gbuf(g_e);
         self->tens[g_e].gwritten = true;
-        self->tens[g_i].gfwritten = true;
+        Target tgi;  // d g_i: fp32 accumulation when g_i is one tensor for all T steps, a plain 16-bit target for a per-chunk copy
+        if (self->tens[g_i].f32acc) self->tens[g_i].gfwritten = true;
+        else if (self->target(g_i, &tgi)) return 1;
         if (!self->dry) {
           ConvDesc d;
           memset(&d, 0, sizeof(d));
@@ -1299,7 +1306,14 @@ struct Engine {
           OutGroup g[2];
           memset(g, 0, sizeof(g));
           g[0].channels = 64;
-          g[0].epi.out_f32 = self->PF(self->tens[g_i].gfoff);
+          if (self->tens[g_i].f32acc) {
+            g[0].epi.out_f32 = self->PF(self->tens[g_i].gfoff);
+          } else {
+            g[0].epi.out = tgi.dst;
+            g[0].epi.pre = tgi.pre;
+            g[0].epi.pre2 = tgi.pre2;
+            g[0].epi.out_f32 = tgi.dstf;
+          }
           g[0].epi.C = 64;
           g[1].channels = 64;
           g[1].epi.out = self->P(self->tens[g_e].goff);
@@ -1310,6 +1324,7 @@ struct Engine {
           g[1].epi.act = ACT_MULT;
           if (self->emit_per_image_conv(d, g, 2, self->P(wd_off), 128, LC_CONV_DGRAD, 2.0 * N * hw * 128 * 64, ":dgrad")) return 1;
         }
+        self->release_consumed();
         self->cur_label = "";
         self->add_pending(xe, self->tens[y].gidx, self->tens[y].goff);
         self->add_pending(xi, self->tens[y].gidx, self->tens[y].goff);
@@ -1331,6 +1346,7 @@ struct Engine {
     c5.in[0] = y;
     c5.in[1] = g4;
     c5.nin = 2;
+    c5.out = u_preset;
     return conv(c5, nm + ".u");
   }
 
@@ -1342,7 +1358,7 @@ struct Engine {
     if (s3 < 0) return 1;
     const float *M = PF(gc.m_off), *sg = PF(gc.s_off);
     float* gw3 = gflat + sites[s3].w_off;
-    const int count = gc.used * B;
+    const int count = (int)gc.used;
     cur_label = sites[s3].key;
     emit([M, sg, count, gw3](cudaStream_t st) { return launch_gate_wgrad(M, sg, count, gw3, st); }, LC_OTHER, 0.0, ":wgrad_gate");
     cur_label = "";
@@ -1388,6 +1404,443 @@ struct Engine {
     if (h < 0) return -1;
     if (out2) *out2 = post >= 0 ? (out2_preset >= 0 ? out2_preset : (int)tens.size() - 1) : -1;
     return h;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // time-chunked, level-major schedule (training plans)
+  // ------------------------------------------------------------------------------------------
+  // Only the three convs of a recurrent trunk depend on the previous time step.  Everything else of an encoder level --
+  // EGACA, the in-conv, fuse_two_dir, the stride-2 `down` conv -- depends on the level below at the SAME step, so on a
+  // training plan (which keeps every step's activations anyway) the sweeps run level by level and those ops run once per
+  // CHUNK of k steps on k*B images instead of once per step: ~8x fewer launches of kernels that are too short (10-45 us at
+  // 64-128 channels and 128^2 .. 64^2 pixels) to amortise their prologue, pipeline fill and tail.  Per-step tensors a chunk
+  // op produces are views of ONE all-T tensor per role, so the per-step consumers (trunks, decoders) and the T-batched
+  // weight gradients of their sites see the same contiguous layout as before.  Image-branch features, which enter every
+  // step, are replicated k times per chunk (`rep`); the backward of that copy sums the k gradient slices.
+  int fuse_all[3] = {-1, -1, -1};  // all-T fuse_two_dir outputs per level (forward sweep)
+  int tchunk = 8;  // steps per chunk (refid_set_option "tchunk" / REFID_TCHUNK; 0: step-major schedule as on forward-only plans)
+
+  // All-T tensor of one per-step role; act / slope describe the producing conv's activation (views inherit the masks).
+  int alloc_all(int N, int Hh, int Ww, int C, int act, float slope, const std::string& name = "") {
+    const int id = new_tensor(N, Hh, Ww, C, name);
+    if (id < 0) return -1;
+    tens[id].act = act;
+    tens[id].slope = slope;
+    if (act == ACT_LRELU) {
+      tens[id].mask_off = tens[id].off;
+      if (train && C % 32 == 0) {  // derivative mask as sign bits (see conv())
+        const int bt = new_tensor(N, Hh, Ww, C / 16);
+        tens[bt].need_grad = false;
+        tens[id].bits_off = tens[bt].off;
+        tens[id].bits_pitch = C / 32;
+      }
+    }
+    return id;
+  }
+
+  // k copies of x along the image axis.  Backward: sum of the k gradient slices -> one pending addend of x.
+  int rep(int x, int k) {
+    const Ten tx = tens[x];
+    if (!tx.contiguous()) {
+      set_error("rep: strided source");
+      return -1;
+    }
+    const int y = new_tensor(k * tx.N, tx.H, tx.W, tx.C);
+    if (y < 0) return -1;
+    const size_t bytes = (size_t)tx.elems() * 2;
+    {
+      const char* src = ws + tx.off;
+      char* dst = ws + tens[y].off;
+      cur_label = "";
+      emit([src, dst, bytes, k](cudaStream_t st) {
+        for (int i = 0; i < k; ++i) REFID_CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)i * bytes, src, bytes, cudaMemcpyDeviceToDevice, st));
+        return 0;
+      }, LC_OTHER, 0.0, "rep");
+    }
+    if (train && tx.need_grad) {
+      Engine* self = this;
+      tape.push_back([self, x, y, k, bytes]() {
+        const __nv_bfloat16* gy = nullptr;
+        if (self->finalize(y, &gy)) return 1;
+        if (!gy) return 0;
+        const int tmp = self->galloc(bytes);
+        __nv_bfloat16* sum = self->P((long)self->gbufs[tmp].off);
+        const long elems = (long)(bytes / 2);
+        self->cur_label = "";
+        self->emit([gy, elems, k, sum](cudaStream_t st) { return launch_sum_series(gy, elems, k, sum, st); }, LC_OTHER, 0.0, "rep:sum");
+        self->release_grad(y);
+        if (self->add_pending(x, tmp, (long)self->gbufs[tmp].off)) return 1;
+        self->gunref(tmp);
+        return 0;
+      });
+    }
+    return y;
+  }
+
+  // Tape hook placed right AFTER a chunk tensor's producer (so it runs right BEFORE the producer's backward): the per-step
+  // views of the chunk only ever receive passthrough addends (skip sums); fold them into the chunk's gradient buffer.
+  void push_flush_hook(int chunk_view, std::vector<int> step_views) {
+    if (!train) return;
+    Engine* self = this;
+    tape.push_back([self, chunk_view, step_views]() {
+      for (int v : step_views) {
+        if (self->tens[v].pending.empty()) continue;
+        if (self->tens[chunk_view].gwritten && !self->tens[v].gwritten) {  // a whole-chunk consumer wrote this region already
+          self->ensure_gbuf(v);
+          self->tens[v].gwritten = true;
+        }
+        if (self->flush_pending(v, false)) return 1;
+      }
+      if (!self->tens[chunk_view].gwritten) {
+        // the step views carried the chunk's only gradients so far: a later whole-chunk write (the producer's own pending
+        // addends) must accumulate -- valid only when every step region has been written
+        int nw = 0;
+        for (int v : step_views) nw += self->tens[v].gwritten ? 1 : 0;
+        REFID_REQUIRE(nw == 0 || nw == (int)step_views.size(), "chunk gradient written for %d of %d steps", nw, (int)step_views.size());
+        if (nw) {
+          self->ensure_gbuf(chunk_view);
+          self->tens[chunk_view].gwritten = true;
+        }
+      }
+      return 0;
+    });
+  }
+  // Tape hook placed right BEFORE the chunk consumer of a recurrent state series (so it runs right AFTER that consumer's
+  // backward, which wrote dL/dh for the chunk's slots of the persistent series gradient array): the per-step state tensors
+  // share that memory, later contributions (the next step's trunk) must accumulate.
+  void push_mark_hook(int chunk_tensor, std::vector<int> step_ids) {
+    if (!train) return;
+    Engine* self = this;
+    tape.push_back([self, chunk_tensor, step_ids]() {
+      if (!self->tens[chunk_tensor].gwritten) return 0;
+      for (int id : step_ids) {
+        self->ensure_gbuf(id);
+        self->tens[id].gwritten = true;
+      }
+      return 0;
+    });
+  }
+
+  // One view id per (all-T tensor, chunk): producer, whole-chunk consumers and the hooks must agree on the id, because the
+  // gradient bookkeeping (written / pending) is kept per tensor id.
+  std::map<std::pair<int, int>, int> cview_cache;
+  int cview(int all_id, int n0, int nk) {
+    auto key = std::make_pair(all_id, n0);
+    auto it = cview_cache.find(key);
+    if (it != cview_cache.end()) return it->second;
+    const int v = view(all_id, n0, nk, 0, tens[all_id].C);
+    cview_cache[key] = v;
+    return v;
+  }
+
+  struct SweepOut {
+    int h_last[3];                 // final recurrent state per level
+    int f_all[3];                  // forward sweep: all-T fuse_two_dir outputs per level
+    bool fuse_deferred[3];         // ... whose gradient w.r.t. the final backward state is computed once, from their sum
+    int d_all[3], x3_all;          // forward sweep: all-T `down` outputs per level, level-2 output + image feature
+    std::vector<std::pair<int, int>> chunks;  // (t0, k) in sweep order
+    std::vector<int> dn[3], cx3;   // forward sweep: per-step views of the `down` outputs and of the level-2 output + image feature
+  };
+
+  // One direction's encoder sweep, level by level, k steps per chunk.  dir 0: t = T-1 .. 0 (XXNet_final_attenfusion_arch.py
+  // :172-181); dir 1: t = 0 .. T-1 with fuse_two_dir against the final backward states hb_final (:185-200).
+  int sweep_chunked(int dir, int u0_all, const int xb[3], int g_i, const int h_series[3], const int h_pad[3], const int* hb_final,
+                    SweepOut* out) {
+    const int b = cfg.base_num_channels;
+    const std::string dname = dir ? "encoders_forward" : "encoders_backward";
+    const std::string dtag = dir ? "f" : "b";
+    int kmax = tchunk;
+    if (kmax * B > 64) kmax = 64 / B;  // per-sample tables of the folded gate live in shared memory (halo-conv epilogue)
+    if (kmax < 1) kmax = 1;
+    struct Chunk { int t0, k; };
+    std::vector<Chunk> chunks;  // in sweep order; images of a chunk are ordered by ascending t
+    if (dir) for (int t0 = 0; t0 < T; t0 += kmax) chunks.push_back({t0, T - t0 < kmax ? T - t0 : kmax});
+    else for (int t1 = T; t1 > 0; t1 -= kmax) chunks.push_back({t1 - kmax > 0 ? t1 - kmax : 0, t1 < kmax ? t1 : kmax});
+    out->chunks.clear();
+    for (const Chunk& ck : chunks) out->chunks.push_back({ck.t0, ck.k});
+    int x_all = -1;  // input of the current level for all T (output of the level below), level >= 1
+    for (int l = 0; l < 3; ++l) {
+      const int Hl = H >> l, Wl = W >> l, Cl = (2 * b) << l;  // trunk resolution / channels
+      const std::string p = dname + "." + std::to_string(l);
+      // all-T tensors of this level's chunk-produced roles
+      int u_all = -1, f_all = -1, d_all = -1, x_next = -1;
+      if (l == 0) u_all = u0_all;
+      else if (l == 1) u_all = alloc_all(T * B, Hl, Wl, Cl, ACT_NONE, 0.f, dtag + ".u1_all");
+      else u_all = alloc_all(T * B, Hl, Wl, Cl, ACT_LRELU, 0.04f, dtag + ".u2_all");
+      if (u_all < 0) return 1;
+      const bool has_down = dir == 1 || l < 2;  // encoders_backward.2.down is dead
+      const bool has_post = has_down && ((dir == 1 && l >= 1) || (dir == 0 && l == 1));
+      if (dir == 1) f_all = alloc_all(T * B, Hl, Wl, Cl, ACT_LRELU, 0.2f, dtag + ".fuse" + std::to_string(l));
+      if (has_down) {
+        d_all = alloc_all(T * B, Hl / 2, Wl / 2, Cl, ACT_NONE, 0.f, dtag + ".dn" + std::to_string(l));
+        x_next = has_post ? alloc_all(T * B, Hl / 2, Wl / 2, Cl, ACT_NONE, 0.f, dtag + ".x" + std::to_string(l + 1)) : d_all;
+        if (d_all < 0 || x_next < 0) return 1;
+      }
+      if (dir == 1) {
+        out->dn[l].assign(T, -1);
+        if (l == 2) out->cx3.assign(T, -1);
+      }
+      // fuse_two_dir reads the final backward state modulo B (no copies) unless a weight-gradient tile of this tiny grid would
+      // span images that do not repeat with period B; then the state is replicated per chunk like the image features
+      bool hb_modulo = dir == 1;
+      for (const Chunk& ck : chunks) {
+        int tw, th, tn;
+        pick_tile(ck.k * B, Hl, Wl, &tw, &th, &tn);
+        if (B % tn) hb_modulo = false;
+      }
+      if (dir == 1) out->fuse_deferred[l] = hb_modulo;
+      int hprev = h_pad[l];
+      // chunk ops on a chunk's states: fuse_two_dir (forward sweep), the stride-2 `down` conv (+ image-feature skip sum).
+      // They are emitted ONE CHUNK LATE (after the next chunk's trunks): the first trunk of the next chunk reads this chunk's
+      // last state, and on the reversed tape its gradient contribution must come AFTER the whole-chunk write of dL/dh by the
+      // chunk consumer's data-gradient (which stores, the per-step contributions accumulate).
+      auto emit_post = [&](int t0, int k, const std::vector<int>& h_ids) -> int {
+        const int n0 = t0 * B, nk = k * B;
+        const int slot0 = dir ? t0 + 1 : t0;
+        const int hc = series_tensor(h_series[l], slot0, nk, Hl, Wl, Cl);
+        series[h_series[l]].need_g = true;
+        push_mark_hook(hc, h_ids);
+        int dsrc = hc;
+        if (dir == 1) {
+          // the final backward state enters every step: the conv reads its B images modulo B, its gradient is ONE 1x1
+          // data-gradient GEMM on the sum of all T output gradients (deferred_state_grad_all, between the sweeps on the tape)
+          ConvOp cf;
+          cf.kind = CK_1X1;
+          cf.site = site(p + ".fuse_two_dir");
+          cf.in[0] = hc;
+          cf.nin = 2;
+          if (hb_modulo) {
+            cf.in[1] = hb_final[l];
+            cf.rep_in1 = cf.defer_in1 = true;
+          } else {
+            cf.in[1] = rep(hb_final[l], k);
+            if (cf.in[1] < 0) return 1;
+          }
+          cf.out = cview(f_all, n0, nk);
+          cf.act = ACT_LRELU;
+          cf.slope = 0.2f;
+          if (conv(cf) < 0) return 1;
+          if (tens[cf.out].bits_off < 0) tens[f_all].bits_off = -1;  // (the conv fell back to an engine without sign bits)
+          dsrc = cf.out;
+        }
+        ConvOp cd;
+        cd.kind = CK_DOWN4;
+        cd.site = site(p + ".down");
+        cd.in[0] = dsrc;
+        cd.out = cview(d_all, n0, nk);
+        if (has_post) {
+          cd.post = rep(xb[l], k);
+          if (cd.post < 0) return 1;
+          cd.out2 = cview(x_next, n0, nk);
+        }
+        if (conv(cd) < 0) return 1;
+        if (dir == 1) {
+          // per-step views for the decoders' skip sums (passthrough addends only: folded in by the hook) and, at level 2,
+          // the bottleneck's input (written through gradient targets)
+          std::vector<int> dviews;
+          for (int i = 0; i < k; ++i) {
+            const int t = t0 + i;
+            out->dn[l][t] = view(d_all, t * B, B, 0, Cl);
+            dviews.push_back(out->dn[l][t]);
+            if (l == 2) out->cx3[t] = view(x_next, t * B, B, 0, Cl);
+          }
+          push_flush_hook(cd.out, dviews);
+        }
+        return 0;
+      };
+      int pend_t0 = -1, pend_k = 0;
+      std::vector<int> pend_ids;
+      for (const Chunk& ck : chunks) {
+        const int t0 = ck.t0, k = ck.k, n0 = t0 * B, nk = k * B;
+        // ---- chunk op: this level's trunk input u for the chunk's k steps
+        if (l == 1) {
+          const int xi_r = rep(xb[0], k), gi_r = rep(g_i, k);
+          if (xi_r < 0 || gi_r < 0) return 1;
+          if (egaca_step(dir, cview(x_all, n0, nk), xi_r, gi_r, dtag + ".c" + std::to_string(t0), cview(u_all, n0, nk)) < 0) return 1;
+        } else if (l == 2) {
+          ConvOp ci;
+          ci.site = site(p + ".conv");
+          ci.in[0] = cview(x_all, n0, nk);
+          ci.out = cview(u_all, n0, nk);
+          ci.act = ACT_LRELU;
+          ci.slope = 0.04f;
+          if (conv(ci) < 0) return 1;
+          if (tens[ci.out].bits_off < 0) tens[u_all].bits_off = -1;
+        }
+        // ---- the recurrent trunks, step by step inside the chunk
+        std::vector<int> h_ids;
+        for (int i = 0; i < k; ++i) {
+          const int t = dir ? t0 + i : t0 + k - 1 - i;
+          cur_slot = dir ? t + 1 : t;
+          cur_sdir = dtag + std::to_string(l);
+          step_seq = 0;
+          const int u = l == 0 ? view(u_all, t * B, B, dir ? 2 * b : 0, 2 * b) : view(u_all, t * B, B, 0, Cl);
+          const std::string nm = dtag + ".t" + std::to_string(t) + ".l" + std::to_string(l);
+          const int hslot = series_tensor(h_series[l], cur_slot, B, Hl, Wl, Cl);
+          const int h = trunk(p + ".recurrent_block.forward_trunk", u, hprev, nm, -1, -1, nullptr, hslot);
+          cur_slot = -1;
+          if (h < 0) return 1;
+          hprev = h;
+          h_ids.push_back(h);
+        }
+        if (!has_down) continue;
+        if (pend_t0 >= 0 && emit_post(pend_t0, pend_k, pend_ids)) return 1;
+        pend_t0 = t0;
+        pend_k = k;
+        pend_ids = h_ids;
+      }
+      if (pend_t0 >= 0 && emit_post(pend_t0, pend_k, pend_ids)) return 1;
+      out->h_last[l] = hprev;
+      out->f_all[l] = f_all;
+      out->d_all[l] = d_all;
+      if (l == 2) out->x3_all = x_next;
+      x_all = x_next;
+    }
+    return 0;
+  }
+
+  // Chunked tail of the forward sweep (training plans): the bottleneck ResidualBlocks and the decoders' transposed convs have
+  // no recurrence either -- at 32^2 .. 64^2 pixels one step is a quarter of a wave of tiles -- so they run per chunk; only
+  // the decoder trunks (and `pred`, which writes the caller's tensor step by step) run per step, level by level.
+  int tail_chunked(const SweepOut& so, int head, int sp_all, int sd[3], const int sd_series[3]) {
+    const int b = cfg.base_num_channels;
+    const int y_all = alloc_all(T * B, H >> 3, W >> 3, 8 * b, ACT_NONE, 0.f, "f.y_all");
+    if (y_all < 0) return 1;
+    for (auto& ck : so.chunks) {
+      const int n0 = ck.first * B, nk = ck.second * B;
+      int xin = cview(so.x3_all, n0, nk);
+      for (int i = 0; i < 2; ++i) {
+        const std::string p = "resblocks." + std::to_string(i);
+        ConvOp c1;
+        c1.site = site(p + ".conv1");
+        c1.in[0] = xin;
+        c1.act = ACT_LRELU;
+        c1.slope = 0.f;
+        const int r = conv(c1);
+        if (r < 0) return 1;
+        ConvOp c2;
+        c2.site = site(p + ".conv2");
+        c2.in[0] = r;
+        c2.res = xin;
+        c2.act = ACT_LRELU;
+        c2.slope = 0.f;
+        if (i == 1) {
+          c2.post = cview(so.d_all[2], n0, nk);
+          c2.out2 = cview(y_all, n0, nk);
+        }
+        const int o = conv(c2);
+        if (o < 0) return 1;
+        xin = (i == 1) ? c2.out2 : o;
+      }
+    }
+    int in_all = y_all;
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "decoders." + std::to_string(i);
+      const int Hd = H >> (2 - i), Wd = W >> (2 - i), Cd = (4 * b) >> i;
+      const int up_all = alloc_all(T * B, Hd, Wd, Cd, ACT_NONE, 0.f, "f.up" + std::to_string(i));
+      const int o2_all = i < 2 ? alloc_all(T * B, Hd, Wd, Cd, ACT_NONE, 0.f, "f.dec" + std::to_string(i)) : sp_all;
+      if (up_all < 0 || o2_all < 0) return 1;
+      for (auto& ck : so.chunks) {
+        const int t0 = ck.first, k = ck.second, n0 = t0 * B, nk = k * B;
+        ConvOp up;
+        up.kind = CK_UP2;
+        up.site = site(p + ".transposed_conv2d");
+        up.in[0] = cview(in_all, n0, nk);
+        up.out = cview(up_all, n0, nk);
+        if (conv(up) < 0) return 1;
+        for (int t = t0; t < t0 + k; ++t) {
+          cur_slot = t + 1;
+          cur_sdir = "fd" + std::to_string(i);
+          step_seq = 0;
+          const std::string nm = "f.t" + std::to_string(t) + ".dec" + std::to_string(i);
+          const int u = view(up_all, t * B, B, 0, Cd);
+          const int post = i < 2 ? so.dn[1 - i][t] : head;
+          const int preset = view(o2_all, t * B, B, 0, Cd);
+          int o2 = -1;
+          const int hs = series_tensor(sd_series[i], t + 1, B, Hd, Wd, Cd);
+          const int st = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2, hs);
+          if (st < 0) {
+            cur_slot = -1;
+            return 1;
+          }
+          sd[i] = st;
+          if (i == 2) {  // prediction for this step straight into the caller's (B,T,out_chn,H,W) tensor
+            ConvOp cp;
+            cp.site = site("pred");
+            cp.in[0] = o2;
+            cp.nchw_out = true;
+            cp.no_tape = true;
+            cp.nchw_toff = (long)t * cfg.out_chn * H * W;
+            cp.nchw_nstride = (long)T * cfg.out_chn * H * W;
+            conv(cp);
+          }
+          cur_slot = -1;
+        }
+      }
+      in_all = o2_all;
+    }
+    return 0;
+  }
+
+  // Per-step tail of the forward sweep: bottleneck ResidualBlocks, the three recurrent decoders and `pred` for step t.
+  // curx = this step's level-2 encoder output (+ image feature), dn[l] = the encoder skips, sd[] = running decoder states.
+  int step_tail(int t, int curx, const int dn[3], int head, int sp_all, int sd[3], const int sd_series[3]) {
+    const int b = cfg.base_num_channels;
+    // bottleneck: two ResidualBlocks (recurrent_sub_modules.py:468-503)
+    int xin = curx;
+    for (int i = 0; i < 2; ++i) {
+      const std::string p = "resblocks." + std::to_string(i);
+      ConvOp c1;
+      c1.site = site(p + ".conv1");
+      c1.in[0] = xin;
+      c1.act = ACT_LRELU;
+      c1.slope = 0.f;
+      const int r = conv(c1);
+      if (r < 0) return 1;
+      ConvOp c2;
+      c2.site = site(p + ".conv2");
+      c2.in[0] = r;
+      c2.res = xin;
+      c2.act = ACT_LRELU;
+      c2.slope = 0.f;
+      if (i == 1) c2.post = dn[2];
+      const int o = conv(c2, "f.t" + std::to_string(t) + ".res" + std::to_string(i));
+      if (o < 0) return 1;
+      xin = (i == 1) ? (int)tens.size() - 1 : o;
+    }
+    // decoders (TransposeRecurrentConvLayer, :370-408); input = previous + encoder skip (skip_sum, :211)
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "decoders." + std::to_string(i);
+      const std::string nm = "f.t" + std::to_string(t) + ".dec" + std::to_string(i);
+      ConvOp up;
+      up.kind = CK_UP2;
+      up.site = site(p + ".transposed_conv2d");
+      up.in[0] = xin;
+      const int u = conv(up, nm + ".up");
+      if (u < 0) return 1;
+      int post, preset = -1, o2 = -1;
+      if (i < 2) {
+        post = dn[1 - i];
+      } else {
+        post = head;
+        if (train) preset = view(sp_all, t * B, B, 0, b);
+      }
+      const int s = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2,
+                          series_tensor(sd_series[i], t + 1, B, H >> (2 - i), W >> (2 - i), (4 * b) >> i));
+      if (s < 0) return 1;
+      sd[i] = s;
+      xin = o2;
+    }
+    // prediction for this step straight into the caller's (B,T,out_chn,H,W) tensor
+    ConvOp cp;
+    cp.site = site("pred");
+    cp.in[0] = xin;
+    cp.nchw_out = true;
+    cp.no_tape = true;
+    cp.nchw_toff = (long)t * cfg.out_chn * H * W;
+    cp.nchw_nstride = (long)T * cfg.out_chn * H * W;
+    conv(cp);
+    return 0;
   }
 
   int build_network() {
@@ -1528,7 +1981,14 @@ struct Engine {
     };
     int hb[3], hb_series[3];
     for (int l = 0; l < 3; ++l) hb_series[l] = state_series(H >> l, W >> l, (2 * b) << l, T, &hb[l]);
-    for (int t = T - 1; t >= 0; --t) {
+    const bool chunked = train && tchunk > 0;  // level-major, time-chunked schedule (see sweep_chunked)
+    SweepOut so_b, so_f;
+    if (chunked) {
+      const int pad[3] = {hb[0], hb[1], hb[2]};
+      if (sweep_chunked(0, u0_all, xb, g_i[0], hb_series, pad, nullptr, &so_b)) return 1;
+      for (int l = 0; l < 3; ++l) hb[l] = so_b.h_last[l];
+    }
+    for (int t = T - 1; t >= 0 && !chunked; --t) {
       cur_slot = t;
       cur_sdir = "b";
       step_seq = 0;
@@ -1573,10 +2033,12 @@ struct Engine {
     // sweeps (i.e. after the whole forward sweep has been back-propagated, before the backward sweep's BPTT starts).
     if (train) {
       const int hb0 = hb[0], hb1 = hb[1], hb2 = hb[2];
-      tape.push_back([self, hb0, hb1, hb2]() {
+      tape.push_back([self, hb0, hb1, hb2, chunked]() {
         const int hbs[3] = {hb0, hb1, hb2};
         for (int l = 0; l < 3; ++l)
-          if (self->deferred_state_grad(l, hbs[l])) return 1;
+          if (chunked ? (self->fuse_all[l] >= 0 && self->deferred_state_grad_all(l, hbs[l], self->fuse_all[l]))
+                      : self->deferred_state_grad(l, hbs[l]))
+            return 1;
         return 0;
       });
     }
@@ -1585,7 +2047,24 @@ struct Engine {
     for (int l = 0; l < 3; ++l) hf_series[l] = state_series(H >> l, W >> l, (2 * b) << l, 0, &hf[l]);
     for (int i = 0; i < 3; ++i) sd_series[i] = state_series(H >> (2 - i), W >> (2 - i), (4 * b) >> i, 0, &sd[i]);
     const int sp_all = train ? new_tensor(T * B, H, W, b, "sp_all") : -1;  // pred's input for all T steps (batched pred backward)
-    for (int t = 0; t < T; ++t) {
+    if (chunked) {
+      const int pad[3] = {hf[0], hf[1], hf[2]};
+      if (sweep_chunked(1, u0_all, xb, g_i[1], hf_series, pad, hb, &so_f)) return 1;
+      for (int l = 0; l < 3; ++l) fuse_all[l] = so_f.fuse_deferred[l] ? so_f.f_all[l] : -1;
+      static const bool step_tail_env = getenv("REFID_STEP_TAIL") != nullptr;  // diagnostic: per-step bottleneck / decoders
+      if (!step_tail_env) {
+        if (tail_chunked(so_f, head, sp_all, sd, sd_series)) return 1;
+      } else {
+        for (int t = 0; t < T; ++t) {
+          cur_slot = t + 1;
+          cur_sdir = "fd";
+          step_seq = 0;
+          const int dn[3] = {so_f.dn[0][t], so_f.dn[1][t], so_f.dn[2][t]};
+          if (step_tail(t, so_f.cx3[t], dn, head, sp_all, sd, sd_series)) return 1;
+        }
+      }
+    }
+    for (int t = 0; t < T && !chunked; ++t) {
       cur_slot = t + 1;
       cur_sdir = "f";
       step_seq = 0;
@@ -1632,60 +2111,7 @@ struct Engine {
         if (dn[l] < 0) return 1;
         curx = (l >= 1) ? (int)tens.size() - 1 : dn[l];
       }
-      // bottleneck: two ResidualBlocks (recurrent_sub_modules.py:468-503)
-      int xin = curx;
-      for (int i = 0; i < 2; ++i) {
-        const std::string p = "resblocks." + std::to_string(i);
-        ConvOp c1;
-        c1.site = site(p + ".conv1");
-        c1.in[0] = xin;
-        c1.act = ACT_LRELU;
-        c1.slope = 0.f;
-        const int r = conv(c1);
-        if (r < 0) return 1;
-        ConvOp c2;
-        c2.site = site(p + ".conv2");
-        c2.in[0] = r;
-        c2.res = xin;
-        c2.act = ACT_LRELU;
-        c2.slope = 0.f;
-        if (i == 1) c2.post = dn[2];
-        const int o = conv(c2, "f.t" + std::to_string(t) + ".res" + std::to_string(i));
-        if (o < 0) return 1;
-        xin = (i == 1) ? (int)tens.size() - 1 : o;
-      }
-      // decoders (TransposeRecurrentConvLayer, :370-408); input = previous + encoder skip (skip_sum, :211)
-      for (int i = 0; i < 3; ++i) {
-        const std::string p = "decoders." + std::to_string(i);
-        const std::string nm = "f.t" + std::to_string(t) + ".dec" + std::to_string(i);
-        ConvOp up;
-        up.kind = CK_UP2;
-        up.site = site(p + ".transposed_conv2d");
-        up.in[0] = xin;
-        const int u = conv(up, nm + ".up");
-        if (u < 0) return 1;
-        int post, preset = -1, o2 = -1;
-        if (i < 2) {
-          post = dn[1 - i];
-        } else {
-          post = head;
-          if (train) preset = view(sp_all, t * B, B, 0, b);
-        }
-        const int s = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2,
-                            series_tensor(sd_series[i], t + 1, B, H >> (2 - i), W >> (2 - i), (4 * b) >> i));
-        if (s < 0) return 1;
-        sd[i] = s;
-        xin = o2;
-      }
-      // prediction for this step straight into the caller's (B,T,out_chn,H,W) tensor
-      ConvOp cp;
-      cp.site = site("pred");
-      cp.in[0] = xin;
-      cp.nchw_out = true;
-      cp.no_tape = true;
-      cp.nchw_toff = (long)t * cfg.out_chn * H * W;
-      cp.nchw_nstride = (long)T * cfg.out_chn * H * W;
-      conv(cp);
+      if (step_tail(t, curx, dn, head, sp_all, sd, sd_series)) return 1;
     }
     cur_slot = -1;
     // pred backward is batched over all T steps: gout -> bf16 NHWC (padded to 32 channels), wgrad + dgrad once
@@ -1743,16 +2169,42 @@ struct Engine {
     const Ten o = tens[calls[0].out];
     const Series& sr = series[o.series];
     REFID_REQUIRE(sr.gbase >= 0 && (int)calls.size() == T, "fuse_two_dir gradients are not kept as a series");
-    cur_label = s.key;
     const long slot_elems = (long)(sr.slot_bytes / 2);
-    const int tmp = galloc(sr.slot_bytes);
-    const __nv_bfloat16* gbase = P(sr.gbase + (long)lo * (long)sr.slot_bytes);
+    return deferred_state_grad_core(s, hb_id, P(sr.gbase + (long)lo * (long)sr.slot_bytes), slot_elems, o);
+  }
+
+  // chunked schedule: the fuse_two_dir outputs of all T steps are ONE tensor (f_all), so are their gradients
+  int deferred_state_grad_all(int l, int hb_id, int f_all) {
+    const int si = site("encoders_forward." + std::to_string(l) + ".fuse_two_dir");
+    if (si < 0) return 1;
+    Ten o = tens[f_all];
+    REFID_REQUIRE(o.goff >= 0 && o.N == T * B, "fuse_two_dir (level %d): no output gradients were written", l);
+    o.N = B;
+    return deferred_state_grad_core(sites[si], hb_id, P(o.goff), o.elems(), o, true);
+  }
+
+  // dL/dh_b = W_h^T . (sum over the T steps of dL/dZ_t): gbase = T consecutive gradient slices of slot_elems elements
+  // as_pending (chunked schedule): the result becomes a pending addend of h_b instead of a write into its gradient buffer --
+  // there the buffer is a slot of the state series' gradient array, which the chunk consumer of the backward sweep (`down`'s
+  // data-gradient over the chunk) STORES into later on the reversed tape.
+  int deferred_state_grad_core(const Site& s, int hb_id, const __nv_bfloat16* gbase, long slot_elems, const Ten& o,
+                               bool as_pending = false) {
+    cur_label = s.key;
+    const int tmp = galloc((size_t)slot_elems * 2);
     __nv_bfloat16* sum = P((long)gbufs[tmp].off);
     const int steps = T;
     emit([gbase, slot_elems, steps, sum](cudaStream_t st) { return launch_sum_series(gbase, slot_elems, steps, sum, st); },
          LC_OTHER, 0.0, ":sum_gz");
     Target t;
-    if (target(hb_id, &t)) return 1;
+    int pend = -1;
+    if (as_pending) {
+      REFID_REQUIRE(tens[hb_id].act == ACT_NONE && tens[hb_id].contiguous(), "deferred state gradient: unexpected state tensor");
+      pend = galloc((size_t)tens[hb_id].elems() * 2);
+      t.dst = P((long)gbufs[pend].off);
+      t.pitch = tens[hb_id].pitch;
+    } else if (target(hb_id, &t)) {
+      return 1;
+    }
     if (!dry) {
       const int c = o.C;  // fuse: (h | h_b) 2c -> c; the data-gradient pack is [2c rows][c cols], h_b rows start at c
       OutGroup g;
@@ -1787,6 +2239,10 @@ struct Engine {
     release_consumed();
     gunref(tmp);
     cur_label = "";
+    if (pend >= 0) {
+      if (add_pending(hb_id, pend, (long)gbufs[pend].off)) return 1;
+      gunref(pend);
+    }
     return 0;
   }
 
@@ -1919,6 +2375,7 @@ struct Engine {
     series_idx.clear();
     site_calls.clear();
     site_batched.clear();
+    cview_cache.clear();
     cur_slot = -1;
     act_top = gtop = 0;
     planned = false;
@@ -1962,6 +2419,7 @@ int refid_create(const refid_cfg* cfg, refid_handle* out) {
   Engine* e = new Engine();
   e->cfg = *cfg;
   if (const char* g = getenv("REFID_GRAPHS")) e->opt_graphs = (g[0] == '0') ? 0 : 1;  // diagnostics (ncu launch lists)
+  if (const char* g = getenv("REFID_TCHUNK")) e->tchunk = atoi(g) < 0 ? 0 : (atoi(g) > 64 ? 64 : atoi(g));
   e->build_sites();
   *out = reinterpret_cast<refid_handle>(e);
   return 0;
@@ -2011,6 +2469,7 @@ int refid_workspace_bytes(refid_handle h, int B, int T, int H, int W, int train,
   Engine tmp;
   tmp.cfg = e->cfg;
   tmp.opt_infer_fp16 = e->opt_infer_fp16;
+  tmp.tchunk = e->tchunk;
   tmp.build_sites();
   if (tmp.plan(B, T, H, W, train, nullptr, nullptr, nullptr, true)) return 1;
   *out = tmp.gbase + tmp.gtop + 4096;
@@ -2066,6 +2525,11 @@ int refid_set_option(refid_handle h, const char* name, long value) {
   Engine* e = reinterpret_cast<Engine*>(h);
   REFID_REQUIRE(e && name, "refid_set_option: null argument");
   const std::string n(name);
+  if (n == "tchunk") {
+    REFID_REQUIRE(value >= 0 && value <= 64, "refid_set_option: tchunk must be in [0, 64]");
+    e->tchunk = (int)value;
+    return 0;
+  }
   if (n == "infer_fp16") {
     REFID_REQUIRE(!e->planned, "refid_set_option: infer_fp16 must be set before refid_plan");
     e->opt_infer_fp16 = value ? 1 : 0;

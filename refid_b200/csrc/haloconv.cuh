@@ -32,6 +32,7 @@ struct HaloConvParams {
   int patch_rows;   // 16*NM + 2*halo
   int wrows_per_tap, w_row0;
   int nsrc, src_slabs[4];
+  int src_nmod[4];  // source s holds src_nmod[s] images that repeat along the launch's image axis (0: off)
   unsigned short slab_mask[16];  // per K slab: taps to execute (0 = all); with `masked`, resident weight tiles are compact
   unsigned char slab_b0[16];     // masked + resident: index of the slab's first weight tile
   int masked, resident_tiles;

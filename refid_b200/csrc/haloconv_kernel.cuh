@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           mbar_wait(&a_empty[sa], ra.ph ^ 1u, 0x700 + sa);
           if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[sa], A_TX);
-            tma_load_4d(a_base + (size_t)sa * A_BYTES, &p.tmA[src], &a_full[sa], slab * KC, x0 - HALO, y0 - HALO, n);
+            tma_load_4d(a_base + (size_t)sa * A_BYTES, &p.tmA[src], &a_full[sa], slab * KC, x0 - HALO, y0 - HALO,
+                        p.src_nmod[src] ? n % p.src_nmod[src] : n);
           }
           ra.advance(SA);
           if (!p.resident_b) {
