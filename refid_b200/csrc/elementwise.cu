@@ -679,6 +679,26 @@ __global__ void __launch_bounds__(kEwThreads) k_sum_series(const __nv_bfloat16* 
   }
 }
 
+// out[t * slot_elems + i] = in[i] for t < k: one read, k writes (image-branch features entering every step of a chunk)
+__global__ void __launch_bounds__(kEwThreads) k_repeat(const uint4* __restrict__ in, long n16, int k, uint4* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) {
+    const uint4 v = in[i];
+    for (int t = 0; t < k; ++t) out[(size_t)t * n16 + i] = v;
+  }
+}
+
+int launch_repeat(const __nv_bfloat16* in, long slot_elems, int k, __nv_bfloat16* out, cudaStream_t s) {
+  REFID_REQUIRE(slot_elems % 8 == 0, "repeat: slot_elems=%ld not a multiple of 8", slot_elems);
+  unsigned blocks = blocks_for(slot_elems / 8, kEwThreads);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  REFID_CUDA_CHECK(launch_k(k_repeat, dim3(blocks), dim3(kEwThreads), 0, s, reinterpret_cast<const uint4*>(in), slot_elems / 8, k,
+                            reinterpret_cast<uint4*>(out)));
+  REFID_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int launch_sum_series(const __nv_bfloat16* base, long slot_elems, int T, __nv_bfloat16* out, cudaStream_t s) {
   REFID_REQUIRE(slot_elems % 8 == 0, "sum_series: slot_elems=%ld not a multiple of 8", slot_elems);
   unsigned blocks = blocks_for(slot_elems / 8, kEwThreads);

@@ -37,6 +37,9 @@ int launch_addmask(const AddMaskArgs& a, cudaStream_t s);
 // out[i] = sum_{t < T} base[t * slot_elems + i]   (fp32 accumulation, bf16 result); slot_elems % 8 == 0.
 int launch_sum_series(const __nv_bfloat16* base, long slot_elems, int T, __nv_bfloat16* out, cudaStream_t s);
 
+// out[t * slot_elems + i] = in[i], t < k (k copies along the image axis); slot_elems % 8 == 0.
+int launch_repeat(const __nv_bfloat16* in, long slot_elems, int k, __nv_bfloat16* out, cudaStream_t s);
+
 // Per-pixel LayerNorm over C = 64 channels without affine (the affine is folded into the following 1x1 conv).
 int launch_ln_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long npix, cudaStream_t s, int f16 = 0);
 // val = d(LN)/dx applied to gy;  dst = (dst_acc ? dst : 0) + add + val   or   dstf += val.

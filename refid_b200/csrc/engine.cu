@@ -1449,13 +1449,11 @@ struct Engine {
     if (y < 0) return -1;
     const size_t bytes = (size_t)tx.elems() * 2;
     {
-      const char* src = ws + tx.off;
-      char* dst = ws + tens[y].off;
+      const __nv_bfloat16* src = P(tx.off);
+      __nv_bfloat16* dst = P(tens[y].off);
+      const long elems = tx.elems();
       cur_label = "";
-      emit([src, dst, bytes, k](cudaStream_t st) {
-        for (int i = 0; i < k; ++i) REFID_CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)i * bytes, src, bytes, cudaMemcpyDeviceToDevice, st));
-        return 0;
-      }, LC_OTHER, 0.0, "rep");
+      emit([src, dst, elems, k](cudaStream_t st) { return launch_repeat(src, elems, k, dst, st); }, LC_OTHER, 0.0, "rep");
     }
     if (train && tx.need_grad) {
       Engine* self = this;
@@ -2295,6 +2293,44 @@ struct Engine {
       Series& sr = series[o0.series];
       if (sr.gbase < 0) sr.gbase = act_alloc(sr.slot_bytes * (size_t)(T + 1));
     }
+    // Chunk ops (time-chunked schedule): the calls of a site write consecutive chunk views of ONE all-T tensor and read
+    // consecutive chunks of one memory range, so the site's weight gradient is again one launch over all T*B images; the
+    // output gradients of all chunks are contiguous in the all-T tensor's gradient buffer (which is never recycled).
+    for (size_t si = 0; si < sites.size(); ++si) {
+      auto& calls = site_calls[si];
+      if (site_batched[si] || calls.size() < 2) continue;
+      bool ok = true;
+      for (auto& c : calls)
+        if (c.out < 0 || c.nchw_out || tens[c.out].parent < 0 || tens[c.out].parent != tens[calls[0].out].parent ||
+            !tens[c.out].contiguous() || c.kind != calls[0].kind || c.nin != calls[0].nin || c.rep_in1 != calls[0].rep_in1)
+          ok = false;
+      if (!ok) continue;
+      std::sort(calls.begin(), calls.end(), [&](const ConvOp& a, const ConvOp& b2) { return tens[a.out].off < tens[b2.out].off; });
+      auto bytes = [&](int id) { return (long)tens[id].N * tens[id].H * tens[id].W * tens[id].pitch * 2; };
+      int rep = 0;
+      long oacc = 0, iacc[2] = {0, 0};
+      for (size_t i = 0; i < calls.size() && ok; ++i) {
+        const Ten& o = tens[calls[i].out];
+        const Ten& o0 = tens[calls[0].out];
+        if (o.off != o0.off + oacc || o.C != o0.C || o.H != o0.H || o.W != o0.W) ok = false;
+        oacc += bytes(calls[i].out);
+        for (int k = 0; k < calls[0].nin && ok; ++k) {
+          const Ten& a0 = tens[calls[0].in[k]];
+          const Ten& a = tens[calls[i].in[k]];
+          if (a.C != a0.C || a.pitch != a0.pitch || a.H != a0.H || a.W != a0.W || !a.contiguous()) ok = false;
+          if (k == 1 && calls[0].rep_in1) {
+            if (a.off != a0.off || a.N != a0.N) ok = false;
+            rep |= 2;
+          } else {
+            if (a.off != a0.off + iacc[k]) ok = false;
+            iacc[k] += bytes(calls[i].in[k]);
+          }
+        }
+      }
+      if (!ok) continue;
+      site_batched[si] = 2;
+      site_rep[si] = rep;
+    }
   }
 
   // Emitted after the whole tape: one bias column-sum and one weight-gradient GEMM per batched site.
@@ -2304,11 +2340,23 @@ struct Engine {
       const Site& s = sites[si];
       const auto& calls = site_calls[si];
       const ConvOp& op = calls[0];
-      const int n = (int)calls.size();
       const Ten o = tens[op.out];
       const Ten in0 = tens[op.in[0]];
-      const Series& sr = series[o.series];
-      const __nv_bfloat16* gz = P(sr.gbase + (long)o.slot * (long)sr.slot_bytes);
+      int n_out = 0, n_in = 0;  // images over all calls (per-step calls: n * B; chunk ops: the chunks' image counts)
+      double flops = 0.0;
+      for (auto& c : calls) {
+        n_out += tens[c.out].N;
+        n_in += tens[c.in[0]].N;
+        flops += conv_flops(c);
+      }
+      const __nv_bfloat16* gz;
+      if (site_batched[si] == 2) {
+        ensure_gbuf(op.out);  // first chunk view -> its region of the all-T tensor's gradient buffer
+        gz = P(tens[op.out].goff);
+      } else {
+        const Series& sr = series[o.series];
+        gz = P(sr.gbase + (long)o.slot * (long)sr.slot_bytes);
+      }
       cur_label = s.key;
       if (dry) continue;
       ConvDesc d;
@@ -2319,7 +2367,7 @@ struct Engine {
         d.kind = CK_UP2_DGRAD;
         d.src[0] = {gz, o.C, o.pitch};
         d.nsrc = 1;
-        d.N = n * o.N;
+        d.N = n_out;
         d.H = o.H;
         d.W = o.W;
         q = {P(in0.off), in0.C, in0.pitch};
@@ -2330,15 +2378,15 @@ struct Engine {
           const Ten& t = tens[op.in[k]];
           d.src[k] = {P(t.off), t.C, t.pitch, (site_rep[si] >> k) & 1 ? t.N : 0};
         }
-        d.N = n * in0.N;
+        d.N = n_in;
         d.H = in0.H;
         d.W = in0.W;
         q = {gz, o.C, o.pitch};
       }
       WgradLaunch wl;
       if (build_wgrad(d, q, gflat + s.w_off, &wl)) return 1;
-      if (s.b_off >= 0 && !wl.bias_done) emit_colsum(gz, (long)n * o.N * o.H * o.W, o.C, gflat + s.b_off);
-      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, conv_flops(op) * n, ":wgrad");
+      if (s.b_off >= 0 && !wl.bias_done) emit_colsum(gz, (long)n_out * o.H * o.W, o.C, gflat + s.b_off);
+      emit([wl](cudaStream_t st) mutable { return run_wgrad(wl, st); }, LC_WGRAD, flops, ":wgrad");
     }
     cur_label = "";
     return 0;

@@ -4,7 +4,7 @@ tag=$1; shift
 mkdir -p gpurun_out
 for cfg in "$@"; do
   echo "== $cfg"
-  env $cfg timeout 600 python bench.py --steps 8 --warmup 3 --no-ref-cuda --no-cpu-baseline 2>/dev/null | python -c "
+  env $cfg timeout 600 python bench.py --steps 12 --warmup 3 --no-ref-cuda --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 r=d['roofline']
