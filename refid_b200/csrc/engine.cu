@@ -93,6 +93,7 @@ struct ConvOp {
   bool no_tape = false;
   bool defer_in1 = false;  // in[1] is the same tensor at every step: its gradient is computed once from the summed dL/dZ
   bool rep_in1 = false;    // in[1] has fewer images than in[0] and repeats along the image axis (chunk ops; implies defer_in1)
+  bool post_no_grad = false;  // the skip-sum addend's gradient is handed over elsewhere (once for all T steps)
 };
 
 typedef std::function<int(cudaStream_t)> Launch;
@@ -872,7 +873,7 @@ struct Engine {
         const int g = tens[op.out2].gidx;
         const long go = tens[op.out2].goff;
         add_pending(op.out, g, go);
-        add_pending(op.post, g, go);
+        if (!op.post_no_grad) add_pending(op.post, g, go);
       }
       release_grad(op.out2);
     }
@@ -1376,7 +1377,7 @@ struct Engine {
   }
 
   int trunk(const std::string& p, int u, int hprev, const std::string& nm, int post, int out2_preset, int* out2,
-            int h_preset = -1) {
+            int h_preset = -1, bool post_no_grad = false) {
     ConvOp a;
     a.site = site(p + ".main.0");
     a.in[0] = u;
@@ -1398,6 +1399,7 @@ struct Engine {
     c.in[0] = r;
     c.res = v;
     c.post = post;
+    c.post_no_grad = post_no_grad;
     c.out2 = out2_preset;
     c.out = h_preset;
     const int h = conv(c, nm + ".h");
@@ -1481,6 +1483,39 @@ struct Engine {
     if (!train) return;
     Engine* self = this;
     tape.push_back([self, chunk_view, step_views]() {
+      // common case: every step view holds exactly one addend and the addends are consecutive in memory (the decoder trunk's
+      // skip-sum gradients, slices of one all-T gradient buffer): ONE masked-accumulate launch over the chunk
+      {
+        bool one = !step_views.empty();
+        const long vb = (long)self->tens[step_views[0]].elems() * 2;
+        for (size_t i = 0; i < step_views.size() && one; ++i) {
+          const Ten& tv = self->tens[step_views[i]];
+          if (tv.pending.size() != 1 || tv.gwritten || tv.pending[0].off != self->tens[step_views[0]].pending[0].off + (long)i * vb) one = false;
+        }
+        if (one && self->tens[chunk_view].contiguous() && self->tens[chunk_view].pending.empty()) {
+          self->ensure_gbuf(chunk_view);
+          AddMaskArgs a = {};
+          a.a = self->P(self->tens[step_views[0]].pending[0].off);
+          if (self->tens[chunk_view].act != ACT_NONE) {
+            a.sv = self->P(self->tens[chunk_view].mask_off);
+            a.act = self->tens[chunk_view].act == ACT_GELU ? ACT_MULT : self->tens[chunk_view].act;
+            a.slope = self->tens[chunk_view].slope;
+          }
+          a.dst = self->P(self->tens[chunk_view].goff);
+          a.dst_acc = self->tens[chunk_view].gwritten ? 1 : 0;
+          a.n = (long)step_views.size() * (vb / 2);
+          self->tens[chunk_view].gwritten = true;
+          const std::string tag = "addmask:flush_chunk:" + std::to_string(self->tens[chunk_view].H) + "x" + std::to_string(self->tens[chunk_view].C);
+          self->emit([a](cudaStream_t s) { return launch_addmask(a, s); }, LC_OTHER, 0.0, tag.c_str());
+          for (int v : step_views) {
+            self->gunref(self->tens[v].pending[0].g);
+            self->tens[v].pending.clear();
+            self->ensure_gbuf(v);
+            self->tens[v].gwritten = true;
+          }
+          return 0;
+        }
+      }
       for (int v : step_views) {
         if (self->tens[v].pending.empty()) continue;
         if (self->tens[chunk_view].gwritten && !self->tens[v].gwritten) {  // a whole-chunk consumer wrote this region already
@@ -1738,6 +1773,26 @@ struct Engine {
       const int up_all = alloc_all(T * B, Hd, Wd, Cd, ACT_NONE, 0.f, "f.up" + std::to_string(i));
       const int o2_all = i < 2 ? alloc_all(T * B, Hd, Wd, Cd, ACT_NONE, 0.f, "f.dec" + std::to_string(i)) : sp_all;
       if (up_all < 0 || o2_all < 0) return 1;
+      if (i == 2 && train && tens[head].need_grad) {
+        // `head` (the image head's output) is the skip-sum addend of EVERY step's last decoder: its gradient is the sum over T
+        // of the gradients of sp_all (one all-T buffer, complete once `pred` and this level have been back-propagated): one
+        // reduction instead of T fp32 read-modify-write passes.  Runs after this level's backward (pushed before its ops).
+        Engine* self = this;
+        const long slot_elems = (long)B * Hd * Wd * Cd;
+        tape.push_back([self, head, sp_all, slot_elems]() {
+          if (self->tens[sp_all].goff < 0) return 0;
+          const int tmp = self->galloc((size_t)slot_elems * 2);
+          __nv_bfloat16* sum = self->P((long)self->gbufs[tmp].off);
+          const __nv_bfloat16* gy = self->P(self->tens[sp_all].goff);
+          const int steps = self->T;
+          self->cur_label = "";
+          self->emit([gy, slot_elems, steps, sum](cudaStream_t st) { return launch_sum_series(gy, slot_elems, steps, sum, st); },
+                     LC_OTHER, 0.0, "head:sum_skip_grads");
+          if (self->add_pending(head, tmp, (long)self->gbufs[tmp].off)) return 1;
+          self->gunref(tmp);
+          return 0;
+        });
+      }
       for (auto& ck : so.chunks) {
         const int t0 = ck.first, k = ck.second, n0 = t0 * B, nk = k * B;
         ConvOp up;
@@ -1756,7 +1811,7 @@ struct Engine {
           const int preset = view(o2_all, t * B, B, 0, Cd);
           int o2 = -1;
           const int hs = series_tensor(sd_series[i], t + 1, B, Hd, Wd, Cd);
-          const int st = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2, hs);
+          const int st = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2, hs, i == 2);
           if (st < 0) {
             cur_slot = -1;
             return 1;
