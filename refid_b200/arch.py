@@ -184,7 +184,9 @@ class _RefidFunction(torch.autograd.Function):
             # Data parallelism: the only collective on the path is this all-reduce (mean) of the flat gradient --
             # one contiguous NCCL call over NVLink/NVSwitch instead of DDP's per-bucket reduction.
             sync_flat_grad(g, group)
-        return None, None, g.clone(), None
+        # `g` is the engine's own flat gradient buffer: the only consumer is _FlatParams.backward, which scatters it into the
+        # per-parameter gradient tensors during this same backward pass (no copy; the buffer is rewritten by the next backward)
+        return None, None, g, None
 
 
 class FinalBidirectionAttenfusion(nn.Module):

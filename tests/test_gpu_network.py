@@ -165,6 +165,15 @@ def test_headline_sequence_length_T23_parity_and_psnr():
     rms_inf = (out.cpu() - ref).pow(2).mean().sqrt().item()
     print(f"T=23 64x64 max-abs error vs fp32 oracle: bf16 training plan {e_train:.3e}; fp16 forward-only {e_inf:.3e} (rms {rms_inf:.3e})")
     assert e_train < 2e-2 and e_inf < 2e-3
+    # context for the north-star's fp32 bar (1e-3): the same fp32 oracle evaluated through PyTorch-CUDA on this GPU against its
+    # CPU evaluation (measured 6e-6: cuDNN keeps these convolutions in fp32, so the bar is about storage precision, not about
+    # summation order -- the network is not chaotic at T = 23)
+    with torch.no_grad():
+        ref_cuda = O.forward({k: v.cuda() for k, v in P.items()}, x.cuda(), ev.cuda()).cpu()
+    e_ref_cuda = (ref_cuda - ref).abs().max().item()
+    print(f"T=23 64x64: the reference's ops through PyTorch-CUDA (fp32) vs their CPU fp32 evaluation: "
+          f"max-abs {e_ref_cuda:.3e}, rms {(ref_cuda - ref).pow(2).mean().sqrt().item():.3e}")
+    assert e_ref_cuda < 1e-4
     p_gpu = metrics.psnr_frames(out[0], gt[0].cuda(), 0)
     p_ref_gpu = metrics.psnr_frames(ref[0].cuda(), gt[0].cuda(), 0)
     worst = 0.0
