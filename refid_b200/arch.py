@@ -248,6 +248,9 @@ class FinalBidirectionAttenfusion(nn.Module):
             self.decoders.append(d)
         self.pred = _conv_layer(b, out_chn, 3, 1)
         self._grad_sync_group = None
+        # time steps per chunk of the level-major training schedule (engine option "tchunk"; None: the engine's default, 8;
+        # 0: step-major).  Not a constructor key: it changes launch order, never results beyond fp32 summation order.
+        self.train_tchunk = None
         self._engines = {}   # device -> Engine (parameter table)
         self._states = {}    # (B,T,H,W,train,device) -> planned engine + buffers
 
@@ -360,6 +363,8 @@ class FinalBidirectionAttenfusion(nn.Module):
         if st is None:
             eng = _engine.Engine(self.img_chn, self.ev_chn, self.out_chn, 32)
             eng.set_option("infer_fp16", self.infer_dtype == 'fp16')
+            if self.train_tchunk is not None:
+                eng.set_option("tchunk", int(self.train_tchunk))
             ws = torch.empty(eng.workspace_bytes(B, T, H, W, train), dtype=torch.uint8, device=device)
             wpack = torch.empty(eng.wpack_bytes, dtype=torch.uint8, device=device)
             grad_flat = torch.zeros(eng.flat_floats, dtype=torch.float32, device=device) if train else None
