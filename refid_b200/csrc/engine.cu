@@ -90,6 +90,8 @@ struct ConvOp {
   int post = -1, out2 = -1;    // out2 = out + post (skip sums)
   bool nchw_out = false;       // pred: fp32 NCHW store into the caller's output tensor
   long nchw_toff = 0, nchw_nstride = 0;
+  int nchw_B = 0;              // > 0: the launch covers a chunk of steps, image n = (step n / B, sample n % B)
+  long nchw_tstride = 0;
   bool no_tape = false;
   bool defer_in1 = false;  // in[1] is the same tensor at every step: its gradient is computed once from the summed dL/dZ
   bool rep_in1 = false;    // in[1] has fewer images than in[0] and repeats along the image axis (chunk ops; implies defer_in1)
@@ -815,6 +817,8 @@ struct Engine {
         e.C = cout;
         e.nchw_C = cfg.out_chn;
         e.nchw_nstride = op.nchw_nstride;
+        e.nchw_B = op.nchw_B;
+        e.nchw_tstride = op.nchw_tstride;
       } else {
         const Ten& o = tens[op.out];
         e.out = P(o.off);
@@ -1006,9 +1010,9 @@ struct Engine {
   // ------------------------------------------------------------------------------------------
   // EGACA pieces (fusion_modules.py:290-333)
   // ------------------------------------------------------------------------------------------
-  int ln(int x, const std::string& name = "") {
+  int ln(int x, const std::string& name = "", int preset = -1) {
     const Ten tx = tens[x];
-    const int y = new_tensor(tx.N, tx.H, tx.W, tx.C, name);
+    const int y = preset >= 0 ? preset : new_tensor(tx.N, tx.H, tx.W, tx.C, name);
     const long npix = (long)tx.N * tx.H * tx.W;
     {
       const __nv_bfloat16 *px = P(tx.off);
@@ -1160,16 +1164,24 @@ struct Engine {
   // sample's conv3 weights by s on their K side, conv3 then reads g_i / g_e directly, and in the backward pass the gate's
   // gradient comes out of a per-sample weight-gradient GEMM -- the gated tensor, its gradient and the two reduction passes
   // over them do not exist (r1: gate_fwd + gate_bwd_reduce + gate_bwd_apply, ~0.3 GB of traffic per call).
-  int egaca_step(int dir, int xe, int xi, int g_i, const std::string& nm, int u_preset = -1) {
+  // Chunk views of all-T tensors for the intermediates that feed 1x1-conv sites (so that those sites' weight gradients are one
+  // launch over all chunks, see decide_batching); -1: per-call allocations.
+  struct EgacaPresets {
+    int n_e, a_e, y, n_y, g4, u;
+    EgacaPresets() : n_e(-1), a_e(-1), y(-1), n_y(-1), g4(-1), u(-1) {}
+  };
+  int egaca_step(int dir, int xe, int xi, int g_i, const std::string& nm) { return egaca_step(dir, xe, xi, g_i, nm, EgacaPresets()); }
+  int egaca_step(int dir, int xe, int xi, int g_i, const std::string& nm, EgacaPresets ps) {
     const std::string a = std::string(dir ? "encoders_forward" : "encoders_backward") + ".1.atten_fuse";
     const Ten te = tens[xe];
     const int N = te.N;
     const long hw = (long)te.H * te.W;
-    const int n_e = ln(xe);
+    const int n_e = ln(xe, "", ps.n_e);
     ConvOp c1;
     c1.kind = CK_1X1;
     c1.site = site(a + ".conv1_e");
     c1.in[0] = n_e;
+    c1.out = ps.a_e;
     const int a_e = conv(c1);
     if (a_e < 0) return -1;
     GateCtx& gc = gate_ctx[dir];
@@ -1211,7 +1223,7 @@ struct Engine {
       emit([pool, parts, inv_hw, sp, sg, mean, z, N](cudaStream_t st) { return launch_se_fwd(pool, parts, inv_hw, sp, sg, mean, z, N, st); }, LC_OTHER, 0.0, ":se_fwd");
     }
     // y = conv3(cat(g_i, g_e)) with this step's per-sample weights, + xe + xi (fusion_modules.py:317-321)
-    const int y = new_tensor(N, te.H, te.W, 64, nm + ".y");
+    const int y = ps.y >= 0 ? ps.y : new_tensor(N, te.H, te.W, 64, nm + ".y");
     {
       ConvDesc d;
       memset(&d, 0, sizeof(d));
@@ -1333,12 +1345,13 @@ struct Engine {
         return 0;
       });
     }
-    const int n_y = ln(y);
+    const int n_y = ln(y, "", ps.n_y);
     ConvOp c4;
     c4.kind = CK_1X1;
     c4.site = site(a + ".conv4");
     c4.in[0] = n_y;
     c4.act = ACT_GELU;
+    c4.out = ps.g4;
     const int g4 = conv(c4);
     if (g4 < 0) return -1;
     ConvOp c5;
@@ -1347,7 +1360,7 @@ struct Engine {
     c5.in[0] = y;
     c5.in[1] = g4;
     c5.nin = 2;
-    c5.out = u_preset;
+    c5.out = ps.u;
     return conv(c5, nm + ".u");
   }
 
@@ -1428,6 +1441,7 @@ struct Engine {
     if (id < 0) return -1;
     tens[id].act = act;
     tens[id].slope = slope;
+    if (act == ACT_GELU && train) tens[id].mask_off = act_alloc((size_t)tens[id].elems() * 2);  // saved gelu'(z)
     if (act == ACT_LRELU) {
       tens[id].mask_off = tens[id].off;
       if (train && C % 32 == 0) {  // derivative mask as sign bits (see conv())
@@ -1622,6 +1636,17 @@ struct Engine {
         if (B % tn) hb_modulo = false;
       }
       if (dir == 1) out->fuse_deferred[l] = hb_modulo;
+      int eg_all[5] = {-1, -1, -1, -1, -1};  // level 1: EGACA intermediates that feed 1x1-conv sites, for all T
+      if (l == 1) {
+        const int Hx = tens[x_all].H, Wx = tens[x_all].W, Cx = tens[x_all].C;
+        eg_all[0] = alloc_all(T * B, Hx, Wx, Cx, ACT_NONE, 0.f);      // LayerNorm(x_e)
+        eg_all[1] = alloc_all(T * B, Hx, Wx, Cx, ACT_NONE, 0.f);      // conv1_e
+        eg_all[2] = alloc_all(T * B, Hx, Wx, Cx, ACT_NONE, 0.f);      // y = conv3(...) + x_e + x_i
+        eg_all[3] = alloc_all(T * B, Hx, Wx, Cx, ACT_NONE, 0.f);      // LayerNorm(y)
+        eg_all[4] = alloc_all(T * B, Hx, Wx, 2 * Cx, ACT_GELU, 0.f);  // GELU(conv4)
+        for (int i = 0; i < 5; ++i)
+          if (eg_all[i] < 0) return 1;
+      }
       int hprev = h_pad[l];
       // chunk ops on a chunk's states: fuse_two_dir (forward sweep), the stride-2 `down` conv (+ image-feature skip sum).
       // They are emitted ONE CHUNK LATE (after the next chunk's trunks): the first trunk of the next chunk reads this chunk's
@@ -1689,7 +1714,14 @@ struct Engine {
         if (l == 1) {
           const int xi_r = rep(xb[0], k), gi_r = rep(g_i, k);
           if (xi_r < 0 || gi_r < 0) return 1;
-          if (egaca_step(dir, cview(x_all, n0, nk), xi_r, gi_r, dtag + ".c" + std::to_string(t0), cview(u_all, n0, nk)) < 0) return 1;
+          EgacaPresets ps;
+          ps.n_e = cview(eg_all[0], n0, nk);
+          ps.a_e = cview(eg_all[1], n0, nk);
+          ps.y = cview(eg_all[2], n0, nk);
+          ps.n_y = cview(eg_all[3], n0, nk);
+          ps.g4 = cview(eg_all[4], n0, nk);
+          ps.u = cview(u_all, n0, nk);
+          if (egaca_step(dir, cview(x_all, n0, nk), xi_r, gi_r, dtag + ".c" + std::to_string(t0), ps) < 0) return 1;
         } else if (l == 2) {
           ConvOp ci;
           ci.site = site(p + ".conv");
@@ -1817,17 +1849,19 @@ struct Engine {
             return 1;
           }
           sd[i] = st;
-          if (i == 2) {  // prediction for this step straight into the caller's (B,T,out_chn,H,W) tensor
-            ConvOp cp;
-            cp.site = site("pred");
-            cp.in[0] = o2;
-            cp.nchw_out = true;
-            cp.no_tape = true;
-            cp.nchw_toff = (long)t * cfg.out_chn * H * W;
-            cp.nchw_nstride = (long)T * cfg.out_chn * H * W;
-            conv(cp);
-          }
           cur_slot = -1;
+        }
+        if (i == 2) {  // prediction for the chunk's steps straight into the caller's (B,T,out_chn,H,W) tensor
+          ConvOp cp;
+          cp.site = site("pred");
+          cp.in[0] = cview(sp_all, n0, nk);
+          cp.nchw_out = true;
+          cp.no_tape = true;
+          cp.nchw_toff = (long)t0 * cfg.out_chn * H * W;
+          cp.nchw_nstride = (long)T * cfg.out_chn * H * W;
+          cp.nchw_B = B;
+          cp.nchw_tstride = (long)cfg.out_chn * H * W;
+          conv(cp);
         }
       }
       in_all = o2_all;

@@ -179,7 +179,9 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
     }
   }
   if (e.out_nchw && cseg == 0) {
-    float* o = e.out_nchw + (size_t)n * e.nchw_nstride + (size_t)y * e.OW + (size_t)x;
+    const size_t nimg = e.nchw_B ? (size_t)(n % e.nchw_B) * e.nchw_nstride + (size_t)(n / e.nchw_B) * e.nchw_tstride
+                                 : (size_t)n * e.nchw_nstride;
+    float* o = e.out_nchw + nimg + (size_t)y * e.OW + (size_t)x;
     const size_t plane = (size_t)e.OH * e.OW;
 #pragma unroll
     for (int i = 0; i < 8; ++i)

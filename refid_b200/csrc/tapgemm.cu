@@ -82,7 +82,9 @@ __device__ __forceinline__ void epi_apply16(const EpiDesc& e, float* v, const fl
   }
   if (e.out) store16<F16>(e.out + base + c0, v);
   if (e.out_nchw && c0 == 0) {
-    float* o = e.out_nchw + (size_t)n * e.nchw_nstride + (size_t)(y * e.osy + e.ooy) * e.OW + (size_t)(x * e.osx + e.oox);
+    const size_t nimg = e.nchw_B ? (size_t)(n % e.nchw_B) * e.nchw_nstride + (size_t)(n / e.nchw_B) * e.nchw_tstride
+                                 : (size_t)n * e.nchw_nstride;
+    float* o = e.out_nchw + nimg + (size_t)(y * e.osy + e.ooy) * e.OW + (size_t)(x * e.osx + e.oox);
     const size_t plane = (size_t)e.OH * e.OW;
 #pragma unroll
     for (int i = 0; i < 16; ++i)

@@ -33,6 +33,8 @@ struct EpiDesc {
   float* out_nchw;      // optional fp32 NCHW store of the first nchw_C channels (pred): [n*nchw_nstride + c*OH*OW + y*OW + x]
   long nchw_nstride;
   int nchw_C;
+  int nchw_B;           // > 0: the launch's image n is (step n / nchw_B, sample n % nchw_B) of a (B,T,C,H,W) tensor:
+  long nchw_tstride;    //      [(n % nchw_B)*nchw_nstride + (n / nchw_B)*nchw_tstride + ...] (a chunk of time steps in one launch)
   const __nv_bfloat16* post;
   const __nv_bfloat16* pre;
   const __nv_bfloat16* pre2;
