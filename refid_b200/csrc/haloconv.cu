@@ -15,7 +15,12 @@ int haloconv_plan(HaloConvParams* p, int BN, int NM, int mode) {
   if (p->n_blocks == 1 && mode != 2 && !p->w_img_rows) {  // (per-image weights are streamed per item)
     p->resident_b = 1;
     p->stages_b = 0;
-    for (int sa = total_slabs >= 3 ? 3 : 2; sa >= 2; --sa) {
+    // activation stages: two for convs with fewer than three K slabs (one tile of look-ahead for the single-slab 64 -> 64
+    // layers), else three.  REFID_HALO_SA = 3 / 4 (diagnostic) tries more: measured neutral without epilogue operands and 3 %
+    // slower with them (tools/conv_bench.py, round 2) -- the activation ring is not what those layers wait for.
+    static const int sa_env = getenv("REFID_HALO_SA") ? atoi(getenv("REFID_HALO_SA")) : 2;
+    const int sa_hi = sa_env <= 2 ? (total_slabs >= 3 ? 3 : 2) : (sa_env > kHaloMaxStages ? kHaloMaxStages : sa_env);
+    for (int sa = sa_hi; sa >= 2; --sa) {
       p->stages_a = sa;
       if (halo_smem_bytes(*p, BN) <= kHaloSmemMax) return 1;
     }
