@@ -95,6 +95,29 @@ def test_workspace_accounting():
         eng.workspace_bytes(1, 2, 30, 32, True)  # H not a multiple of 8: reported, not silently handled
 
 
+def test_time_chunked_plans_build_for_every_chunk_size():
+    """Dry plans (no GPU) of the level-major, time-chunked training schedule: every chunk size plans -- including partial
+    last chunks, one step per chunk and chunks longer than T --, the step-major schedule stays available, and the extra
+    all-T gradient buffers keep the workspace within 10 % of the step-major plan."""
+    from refid_b200 import engine
+    eng = engine.Engine(26, 2)
+    eng.set_option("tchunk", 0)
+    base = eng.workspace_bytes(8, 23, 256, 256, True)
+    small0 = eng.workspace_bytes(2, 5, 64, 64, True)
+    for k in (1, 2, 3, 5, 8, 23, 64):
+        eng.set_option("tchunk", k)
+        assert 0.9 * base < eng.workspace_bytes(8, 23, 256, 256, True) < 1.1 * base, k
+        assert 0.8 * small0 < eng.workspace_bytes(2, 5, 64, 64, True) < 1.25 * small0, k
+        assert eng.workspace_bytes(1, 1, 32, 32, True) > 0
+    with pytest.raises(RuntimeError):
+        eng.set_option("tchunk", 65)
+    # forward-only plans do not depend on the option (they keep the step-major order and O(1)-in-T workspace)
+    eng.set_option("tchunk", 0)
+    a = eng.workspace_bytes(1, 15, 720, 1280, False)
+    eng.set_option("tchunk", 8)
+    assert eng.workspace_bytes(1, 15, 720, 1280, False) == a
+
+
 def test_bf16_emulating_oracle_is_a_restatement_of_the_same_network():
     from oracle import refid_oracle_bf16 as OB
     P = paramgen.make_params(O.param_shapes(6, 2))
