@@ -33,6 +33,11 @@ struct EpiPF {
   uint32_t m;        // activation sign bits of the 32 channels (sv_bits)
 };
 
+// LEAN instantiations serve launches whose epilogues only use {bias, pre, sign-bit masks, LeakyReLU / none, out}: the forms of
+// most trunk convs.  Everything else (second addend, 16-bit masks, GELU, skip-sum second output, fp32 / NCHW targets) is
+// compiled out, which shortens the hot loop body to what the instruction cache holds and frees the second operand set's
+// registers (ncu: 0.6-1.1 stall cycles per issued instruction were instruction fetch in the general kernel).
+template <bool LEAN>
 __device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, size_t pix, int cword, bool valid, EpiPF& f) {
   if (!valid) return;
   if (e.sv_bits) f.m = __ldg(e.sv_bits + pix * (size_t)e.sv_bits_pitch + cword);
@@ -40,10 +45,12 @@ __device__ __forceinline__ void epi_prefetch32(const EpiDesc& e, size_t off, siz
     ldg256(e.pre + off, f.a[0], f.a[1]);
     ldg256(e.pre + off + 16, f.a[2], f.a[3]);
   }
-  const __nv_bfloat16* third = e.sv ? e.sv : e.post;
-  if (third) {
-    ldg256(third + off, f.c[0], f.c[1]);
-    ldg256(third + off + 16, f.c[2], f.c[3]);
+  if (!LEAN) {
+    const __nv_bfloat16* third = e.sv ? e.sv : e.post;
+    if (third) {
+      ldg256(third + off, f.c[0], f.c[1]);
+      ldg256(third + off + 16, f.c[2], f.c[3]);
+    }
   }
 }
 
@@ -106,7 +113,7 @@ __device__ __forceinline__ void store32(__nv_bfloat16* ptr, const float* v) {
 // global operands taken from registers (prefetched from global memory or read from the TMA-staged tiles).  On return
 // v = the `out` values and, when e.out2, v2 = out + post.  The rare fp32 / NCHW / pre-activation outputs are written here.
 // GELU (exact erf: ~60 instructions per element, twice) is compiled only into the GELU instantiations.
-template <bool GELU, bool INPUTS, bool F16>
+template <bool GELU, bool INPUTS, bool F16, bool LEAN>
 __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2, size_t off, int cseg, int n, int y, int x,
                                            const EpiPF& f, const float* sbias, uint32_t* bits_dst, bool f32_rmw) {
   if (e.bias) {  // bias table of the launch in shared memory (with ~227 KB of smem in use the L1 is too small to cache it)
@@ -121,7 +128,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
 #pragma unroll
     for (int k = 0; k < 4; ++k) add_chunk8<F16>(v + 8 * k, f.a[k]);
   }
-  if (INPUTS && e.pre2) {
+  if (INPUTS && !LEAN && e.pre2) {
     uint4 r[4];
     ldg256(e.pre2 + off, r[0], r[1]);
     ldg256(e.pre2 + off + 16, r[2], r[3]);
@@ -133,7 +140,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
     const uint32_t m = f.m;
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= ((m >> i) & 1u) ? 1.f : sl;
-  } else if (INPUTS && e.sv) {
+  } else if (INPUTS && !LEAN && e.sv) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -148,7 +155,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       }
     }
   } else {
-    if (GELU && e.act == ACT_GELU) {
+    if (GELU && !LEAN && e.act == ACT_GELU) {
       // out = gelu(z); out_pre = gelu'(z) for the backward pass (chunk-wise: 8 temporaries)
 #pragma unroll
       if (e.out_pre) {
@@ -164,7 +171,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
         for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
       }
     } else {
-      if (e.out_pre) store32<F16>(e.out_pre + off, v);
+      if (!LEAN && e.out_pre) store32<F16>(e.out_pre + off, v);
       if (e.act == ACT_LRELU) {
         const float sl = e.slope;
         if (bits_dst) {  // training plans: the derivative mask as sign bits (see EpiDesc)
@@ -178,7 +185,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       }
     }
   }
-  if (e.out_nchw && cseg == 0) {
+  if (!LEAN && e.out_nchw && cseg == 0) {
     const size_t nimg = e.nchw_B ? (size_t)(n % e.nchw_B) * e.nchw_nstride + (size_t)(n / e.nchw_B) * e.nchw_tstride
                                  : (size_t)n * e.nchw_nstride;
     float* o = e.out_nchw + nimg + (size_t)y * e.OW + (size_t)x;
@@ -187,7 +194,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
     for (int i = 0; i < 8; ++i)
       if (i < e.nchw_C) o[i * plane] = v[i];
   }
-  if (e.out_f32) {
+  if (!LEAN && e.out_f32) {
     // fp32 accumulation target: fire-and-forget vector reductions (the add happens in the L2; no load, no exposed latency --
     // the read-modify-write version stalled ~1 us per 32-channel group).  Every element receives exactly ONE add per launch
     // and launches are stream-ordered, so the result does not depend on any ordering.
@@ -219,7 +226,7 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
 // so the single issuing thread has <= 62 cycles per MMA at N <= 128.  The producer and MMA warps therefore run their
 // loops warp-uniformly (warp index via shuffle, elect.sync only around the issue) so that descriptors live in uniform
 // registers, and every per-MMA descriptor is `base + compile-time constant` (TAPS / pitch / NM are template parameters).
-template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16>
+template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16, bool LEAN>
 __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PITCH = TAPS == 9 ? 10 : 8;       // pixels per patch row in shared memory
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           int cseg, y, cword;
           bool valid;
           group_ctx(g, e, off, pix, cword, cseg, y, valid);
-          epi_prefetch32(*e, off, pix, cword, valid, f);
+          epi_prefetch32<LEAN>(*e, off, pix, cword, valid, f);
         };
         auto process = [&](int g, const EpiPF& f) {
           const EpiDesc* e;
@@ -566,18 +573,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           tmem_ld16(taddr + 16, v + 16);
           tmem_ld_wait();
           if (valid) {
-            epi_math32<GELU, INPUTS, F16>(*e, v, nullptr, off, cseg, n, y, x, f,
+            epi_math32<GELU, INPUTS, F16, LEAN>(*e, v, nullptr, off, cseg, n, y, x, f,
                                           sbias + (p.bias_images ? n * bias_row : 0) + nblk * BN + c0,
                                           e->out_bits ? e->out_bits + pix * (size_t)e->out_bits_pitch + cword : nullptr,
                                           p.f32_rmw != 0);
             if (e->out) store32<F16>(e->out + off, v);
-            if (INPUTS && e->out2) store32_sum<F16>(e->out2 + off, v, f.c);
+            if (INPUTS && !LEAN && e->out2) store32_sum<F16>(e->out2 + off, v, f.c);
           }
         };
         // L2 prefetch of the NEXT item's epilogue operands (residuals, masks, skip-sum addends): they are whole activation
         // tensors streamed from HBM; the register prefetch below covers two groups (~1-2 k cycles), which under a loaded
         // memory system is about one DRAM round trip -- with the lines already in L2 it covers the rest comfortably
-        if (INPUTS && p.epi_l2pf) {
+        if (INPUTS && !LEAN && p.epi_l2pf) {
           const int item2 = item + (int)gridDim.x;
           if (item2 < p.num_items) {
             const int nblk2 = item2 % p.n_blocks, tile2 = item2 / p.n_blocks;
@@ -650,11 +657,11 @@ inline size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
 }
 
 
-template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16>
+template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16, bool LEAN>
 int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
     configured = true;
   }
   static int num_sms = 0;
@@ -664,7 +671,7 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
     REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  REFID_CUDA_CHECK(launch_k(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16>, dim3(grid), dim3(kHaloThreads), halo_smem_bytes(p, BN), stream, p));
+  REFID_CUDA_CHECK(launch_k(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN>, dim3(grid), dim3(kHaloThreads), halo_smem_bytes(p, BN), stream, p));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -679,17 +686,31 @@ int launch_haloconv_flavour(const HaloConvParams& p, int BN, int NM, cudaStream_
   for (int i = 0; i < kMaxNBlocks; ++i) gelu = gelu || p.epi[i].act == ACT_GELU;
   REFID_REQUIRE(!gelu || (p.num_taps == 1 && p.kc == 64), "haloconv: GELU epilogues are instantiated for 1x1 / 64-channel slabs only");
   const bool in = p.epi_inputs != 0;
+  // lean epilogue: only {bias, pre, sign-bit masks, LeakyReLU / none, out} anywhere in the launch (3x3 convs only: the 1x1
+  // launches are HBM-bound and mostly carry other features)
+  bool lean = p.num_taps == 9 && !p.epi_l2pf && !p.f32_rmw && !gelu;
+  static const int no_lean = getenv("REFID_NO_LEAN") ? 1 : 0;
+  if (no_lean) lean = false;
+  for (int i = 0; i < kMaxNBlocks && lean; ++i) {
+    const EpiDesc& e = p.epi[i];
+    if (e.out_nchw || e.out_f32 || e.pre2 || e.sv || e.post || e.out2 || e.out_pre || (e.act != ACT_NONE && e.act != ACT_LRELU)) lean = false;
+  }
 #define HPICK(bn, nm, taps, kc, gl) \
-  return in ? launch_halo_inst<bn, nm, taps, kc, gl, true, F16>(p, stream) : launch_halo_inst<bn, nm, taps, kc, gl, false, F16>(p, stream)
+  return in ? launch_halo_inst<bn, nm, taps, kc, gl, true, F16, false>(p, stream) : launch_halo_inst<bn, nm, taps, kc, gl, false, F16, false>(p, stream)
+#define HPICK9(bn, nm, kc)                                                                                                   \
+  return lean ? (in ? launch_halo_inst<bn, nm, 9, kc, false, true, F16, true>(p, stream)                                      \
+                    : launch_halo_inst<bn, nm, 9, kc, false, false, F16, true>(p, stream))                                    \
+              : (in ? launch_halo_inst<bn, nm, 9, kc, false, true, F16, false>(p, stream)                                     \
+                    : launch_halo_inst<bn, nm, 9, kc, false, false, F16, false>(p, stream))
 #define HINST(bn, nm)                                \
   if (BN == bn && NM == nm && p.kc == 64) {         \
-    if (p.num_taps == 9) HPICK(bn, nm, 9, 64, false); \
+    if (p.num_taps == 9) HPICK9(bn, nm, 64);         \
     if (gelu) HPICK(bn, nm, 1, 64, true);            \
     HPICK(bn, nm, 1, 64, false);                     \
   }
 #define HINST32(bn, nm)                              \
   if (BN == bn && NM == nm && p.kc == 32) {         \
-    if (p.num_taps == 9) HPICK(bn, nm, 9, 32, false); \
+    if (p.num_taps == 9) HPICK9(bn, nm, 32);         \
     HPICK(bn, nm, 1, 32, false);                     \
   }
   HINST(32, 1) HINST(64, 1) HINST(128, 1) HINST(256, 1)
@@ -697,6 +718,7 @@ int launch_haloconv_flavour(const HaloConvParams& p, int BN, int NM, cudaStream_
   HINST32(32, 1) HINST32(64, 1) HINST32(128, 1)
   HINST32(32, 2) HINST32(64, 2) HINST32(128, 2)
 #undef HPICK
+#undef HPICK9
 #undef HINST32
 #undef HINST
   set_error("haloconv: unsupported BN=%d NM=%d", BN, NM);
