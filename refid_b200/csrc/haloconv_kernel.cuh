@@ -686,32 +686,42 @@ int launch_haloconv_flavour(const HaloConvParams& p, int BN, int NM, cudaStream_
   for (int i = 0; i < kMaxNBlocks; ++i) gelu = gelu || p.epi[i].act == ACT_GELU;
   REFID_REQUIRE(!gelu || (p.num_taps == 1 && p.kc == 64), "haloconv: GELU epilogues are instantiated for 1x1 / 64-channel slabs only");
   const bool in = p.epi_inputs != 0;
-  // lean epilogue: only {bias, pre, sign-bit masks, LeakyReLU / none, out} anywhere in the launch (3x3 convs only: the 1x1
-  // launches are HBM-bound and mostly carry other features)
-  bool lean = p.num_taps == 9 && !p.epi_l2pf && !p.f32_rmw && !gelu;
+  // lean epilogue: only {bias, pre, sign-bit masks, LeakyReLU / none, out} anywhere in the launch
+  bool lean = !p.epi_l2pf && !p.f32_rmw && !gelu;
   static const int no_lean = getenv("REFID_NO_LEAN") ? 1 : 0;
   if (no_lean) lean = false;
   for (int i = 0; i < kMaxNBlocks && lean; ++i) {
     const EpiDesc& e = p.epi[i];
     if (e.out_nchw || e.out_f32 || e.pre2 || e.sv || e.post || e.out2 || e.out_pre || (e.act != ACT_NONE && e.act != ACT_LRELU)) lean = false;
   }
+  static const int census = getenv("REFID_EPI_CENSUS") ? 1 : 0;  // diagnostic: which epilogue features launches use
+  if (census) {
+    unsigned f = 0;
+    for (int i = 0; i < kMaxNBlocks; ++i) {
+      const EpiDesc& e = p.epi[i];
+      f |= (e.pre ? 1u : 0) | (e.pre2 ? 2u : 0) | (e.sv ? 4u : 0) | (e.sv_bits ? 8u : 0) | (e.post || e.out2 ? 16u : 0) |
+           (e.out_pre ? 32u : 0) | (e.out_f32 ? 64u : 0) | (e.out_nchw ? 128u : 0) | (e.act == ACT_GELU ? 256u : 0) |
+           (e.act == ACT_MULT ? 512u : 0) | (e.out_bits ? 1024u : 0) | (e.osx > 1 ? 2048u : 0);
+    }
+    fprintf(stderr, "EPI_CENSUS taps=%d kc=%d BN=%d NM=%d items=%d feat=0x%x lean=%d\n", p.num_taps, p.kc, BN, NM, p.num_items, f, (int)lean);
+  }
 #define HPICK(bn, nm, taps, kc, gl) \
   return in ? launch_halo_inst<bn, nm, taps, kc, gl, true, F16, false>(p, stream) : launch_halo_inst<bn, nm, taps, kc, gl, false, F16, false>(p, stream)
-#define HPICK9(bn, nm, kc)                                                                                                   \
-  return lean ? (in ? launch_halo_inst<bn, nm, 9, kc, false, true, F16, true>(p, stream)                                      \
-                    : launch_halo_inst<bn, nm, 9, kc, false, false, F16, true>(p, stream))                                    \
-              : (in ? launch_halo_inst<bn, nm, 9, kc, false, true, F16, false>(p, stream)                                     \
-                    : launch_halo_inst<bn, nm, 9, kc, false, false, F16, false>(p, stream))
+#define HPICK9(bn, nm, taps, kc)                                                                                             \
+  return lean ? (in ? launch_halo_inst<bn, nm, taps, kc, false, true, F16, true>(p, stream)                                   \
+                    : launch_halo_inst<bn, nm, taps, kc, false, false, F16, true>(p, stream))                                 \
+              : (in ? launch_halo_inst<bn, nm, taps, kc, false, true, F16, false>(p, stream)                                  \
+                    : launch_halo_inst<bn, nm, taps, kc, false, false, F16, false>(p, stream))
 #define HINST(bn, nm)                                \
   if (BN == bn && NM == nm && p.kc == 64) {         \
-    if (p.num_taps == 9) HPICK9(bn, nm, 64);         \
+    if (p.num_taps == 9) HPICK9(bn, nm, 9, 64);      \
     if (gelu) HPICK(bn, nm, 1, 64, true);            \
-    HPICK(bn, nm, 1, 64, false);                     \
+    HPICK9(bn, nm, 1, 64);                           \
   }
 #define HINST32(bn, nm)                              \
   if (BN == bn && NM == nm && p.kc == 32) {         \
-    if (p.num_taps == 9) HPICK9(bn, nm, 32);         \
-    HPICK(bn, nm, 1, 32, false);                     \
+    if (p.num_taps == 9) HPICK9(bn, nm, 9, 32);      \
+    HPICK9(bn, nm, 1, 32);                           \
   }
   HINST(32, 1) HINST(64, 1) HINST(128, 1) HINST(256, 1)
   HINST(32, 2) HINST(64, 2) HINST(128, 2)
