@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_PATH = os.path.join(_HERE, "librefid_b200.so")
+_PATH = os.environ.get("REFID_LIB") or os.path.join(_HERE, "librefid_b200.so")  # REFID_LIB: A/B of two builds (diagnostic)
 _lib = None
 
 c_void_p, c_int, c_long, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float

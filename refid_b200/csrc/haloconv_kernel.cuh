@@ -117,10 +117,11 @@ template <bool GELU, bool INPUTS, bool F16, bool LEAN>
 __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2, size_t off, int cseg, int n, int y, int x,
                                            const EpiPF& f, const float* sbias, uint32_t* bits_dst, bool f32_rmw) {
   if (e.bias) {  // bias table of the launch in shared memory (with ~227 KB of smem in use the L1 is too small to cache it)
-    const float4* b4 = reinterpret_cast<const float4*>(sbias);
+    const uint32_t b4 = smem_u32(sbias);  // explicit shared-space loads (the pointer would otherwise be treated as generic)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 t = b4[i];
+      float4 t;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(b4 + 16 * i));
       v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
     }
   }
@@ -174,14 +175,19 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
       if (!LEAN && e.out_pre) store32<F16>(e.out_pre + off, v);
       if (e.act == ACT_LRELU) {
         const float sl = e.slope;
-        if (bits_dst) {  // training plans: the derivative mask as sign bits (see EpiDesc)
+        if (bits_dst) {  // training plans: the derivative mask as sign bits (see EpiDesc); one compare serves mask and value
           uint32_t m = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f ? 1u : 0u) << i;
+          for (int i = 0; i < 32; ++i) {
+            const bool pos = v[i] > 0.f;
+            m |= (pos ? 1u : 0u) << i;
+            v[i] = pos ? v[i] : v[i] * sl;
+          }
           *bits_dst = m;
-        }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+        }
       }
     }
   }
