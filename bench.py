@@ -438,7 +438,7 @@ def main():
             tot = sum(v["ms"] for v in prof.values())
             ach = cfl / (cms * 1e-3) / 1e12
             traffic = None
-            for name in ("r02_ncu_haloconv3x3.json", "r01_ncu_haloconv.json"):
+            for name in ("r02_ncu_haloconv3x3_lean.json", "r02_ncu_haloconv3x3.json", "r01_ncu_haloconv.json"):
                 tp = os.path.join(ROOT, "profiles", name)
                 if os.path.exists(tp):  # dram bytes per launch from the committed `ncu --set full` capture of the same kernel
                     caps = [c for c in json.load(open(tp)) if "haloconv" in c.get("kernel", "")]
