@@ -164,7 +164,7 @@ struct Engine {
     unsigned long stamp = 0;
     int seen = 0;
   };
-  static constexpr int kGraphSlots = 4;
+  static constexpr int kGraphSlots = 8;
   GraphSlot fwd_graphs[kGraphSlots], bwd_graphs[kGraphSlots];
   unsigned long graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
