@@ -92,9 +92,9 @@ int refid_flat_scatter(const refid_flat_entry* entries, int n, const float* gfla
  *       output within ~1e-3 max-abs / 2.5e-4 RMS of the fp32 reference (the PSNR-parity bar); training plans are bf16.
  *   "graphs" (default 1): refid_forward / refid_backward replay their launch list as a CUDA graph once the same
  *       (x, event, out) / grad_out pointers are seen a second time; 0 = plain launches.
- *   "tchunk" (default 8; set before refid_plan / refid_workspace_bytes; env REFID_TCHUNK): training plans run the two
+ *   "tchunk" (default 64, i.e. as many as the limit allows; set before refid_plan / refid_workspace_bytes; env REFID_TCHUNK): training plans run the two
  *       sweeps level by level and every op without a recurrence (EGACA, in-convs, fuse_two_dir, `down`, bottleneck,
- *       transposed convs) once per chunk of `tchunk` time steps on tchunk*B images instead of once per step; only the
+ *       transposed convs) once per chunk of min(tchunk, 64 / B, T) time steps on that many x B images instead of once per step; only the
  *       recurrent trunks run step by step.  0 = the step-major schedule (the order of the reference's Python loop, which
  *       forward-only plans always use).  Results are identical up to fp32 summation order of the weight gradients.
  * refid_graph_stats: {graphs captured, graph replays, eager runs, capture failures}.  refid_plan_storage: 1 = the current

@@ -248,7 +248,7 @@ class FinalBidirectionAttenfusion(nn.Module):
             self.decoders.append(d)
         self.pred = _conv_layer(b, out_chn, 3, 1)
         self._grad_sync_group = None
-        # time steps per chunk of the level-major training schedule (engine option "tchunk"; None: the engine's default, 8;
+        # time steps per chunk of the level-major training schedule (engine option "tchunk"; None: the engine's default, as many as fit;
         # 0: step-major).  Not a constructor key: it changes launch order, never results beyond fp32 summation order.
         self.train_tchunk = None
         self._engines = {}   # device -> Engine (parameter table)
