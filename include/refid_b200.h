@@ -94,7 +94,7 @@ int refid_flat_scatter(const refid_flat_entry* entries, int n, const float* gfla
  *       (x, event, out) / grad_out pointers are seen a second time; 0 = plain launches.
  *   "tchunk" (default 64, i.e. as many as the limit allows; set before refid_plan / refid_workspace_bytes; env REFID_TCHUNK): training plans run the two
  *       sweeps level by level and every op without a recurrence (EGACA, in-convs, fuse_two_dir, `down`, bottleneck,
- *       transposed convs) once per chunk of min(tchunk, 64 / B, T) time steps on that many x B images instead of once per step; only the
+ *       transposed convs) once per chunk of min(tchunk, 192 / B, T) time steps on that many x B images instead of once per step; only the
  *       recurrent trunks run step by step.  0 = the step-major schedule (the order of the reference's Python loop, which
  *       forward-only plans always use).  Results are identical up to fp32 summation order of the weight gradients.
  * refid_graph_stats: {graphs captured, graph replays, eager runs, capture failures}.  refid_plan_storage: 1 = the current

@@ -127,7 +127,7 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   h.w_img_rows = d.w_img_rows;
   for (int g = 0; g < ngroups; ++g)
     if (groups[g].epi.bias && groups[g].epi.bias_nstride) h.bias_images = d.N;
-  if (h.bias_images && (size_t)h.bias_images * total * 4 > 32 * 1024) return 0;  // per-sample bias table must fit shared memory
+  if (h.bias_images && (size_t)h.bias_images * total * 4 > kHaloMaxBiasTable) return 0;  // per-sample bias table must fit shared memory
   h.num_taps = (d.kind == CK_1X1 || up2) ? 1 : 9;
   h.halo = (d.kind == CK_1X1 || up2) ? 0 : 1;
   h.pitch_px = h.halo ? 10 : 8;

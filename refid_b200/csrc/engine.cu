@@ -1434,8 +1434,8 @@ struct Engine {
   // step, are replicated k times per chunk (`rep`); the backward of that copy sums the k gradient slices.
   int fuse_all[3] = {-1, -1, -1};  // all-T fuse_two_dir outputs per level (forward sweep)
   // steps per chunk (refid_set_option "tchunk" / REFID_TCHUNK; 0: step-major schedule as on forward-only plans).  The default
-  // asks for as many as the 64-image limit of EGACA's per-sample tables allows: 8 at B = 8, all T at B <= 2 (measured at
-  // B = 1: 749 -> 783 frames/s against chunks of 8; HighREV B = 2: 348 -> 357)
+  // asks for as many as the 192-image limit of EGACA's per-sample tables allows: all T = 23 at B = 8 (measured at B = 1:
+  // 749 -> 783 frames/s against chunks of 8; HighREV B = 2: 348 -> 357; B = 8: 126.7 -> 125.0 ms)
   int tchunk = 64;
 
   // All-T tensor of one per-step role; act / slope describe the producing conv's activation (views inherit the masks).
@@ -1600,7 +1600,9 @@ struct Engine {
     const std::string dname = dir ? "encoders_forward" : "encoders_backward";
     const std::string dtag = dir ? "f" : "b";
     int kmax = tchunk;
-    if (kmax * B > 64) kmax = 64 / B;  // per-sample tables of the folded gate live in shared memory (halo-conv epilogue)
+    // per-sample tables of the folded gate live in shared memory (halo-conv epilogue): 512 bytes per image of the chunk
+    const int max_imgs = (int)(kHaloMaxBiasTable / 512);
+    if (kmax * B > max_imgs) kmax = max_imgs / B;
     if (kmax < 1) kmax = 1;
     struct Chunk { int t0, k; };
     std::vector<Chunk> chunks;  // in sweep order; images of a chunk are ordered by ascending t

@@ -6,6 +6,11 @@ namespace refid {
 int launch_haloconv_f16(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);  // haloconv_f16.cu
 
 
+size_t halo_max_bias_table() {
+  static const size_t v = getenv("REFID_BIAS_KB") ? (size_t)atoi(getenv("REFID_BIAS_KB")) * 1024 : 96 * 1024;
+  return v;
+}
+
 int haloconv_plan(HaloConvParams* p, int BN, int NM, int mode) {
   if (2 * NM * BN > 512) return 0;
   p->patch_rows = 16 * NM + 2 * p->halo;

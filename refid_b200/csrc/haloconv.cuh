@@ -48,6 +48,11 @@ struct HaloConvParams {
   int f32_rmw;      // diagnostic: fp32 accumulation targets by read-modify-write instead of vector reductions
 };
 
+// Largest per-sample bias table (one row of n_blocks*BN floats per image) a launch may keep in shared memory.  REFID_BIAS_KB
+// (diagnostic) overrides the default of 96 KB (192 images x 128 channels: EGACA's data-gradient over a chunk of time steps;
+// all 23 steps of the benchmark batch of 8 -- measured 1 % faster than chunks of 8 steps with a 32 KB table).
+size_t halo_max_bias_table();
+#define kHaloMaxBiasTable (::refid::halo_max_bias_table())
 int launch_haloconv(const HaloConvParams& p, int BN, int NM, cudaStream_t stream);
 // Shared-memory plan; returns 0 when the configuration does not fit.  mode 0: resident weights if they fit, else
 // streamed; 1: resident only; 2: streamed only.
