@@ -21,7 +21,12 @@ static __device__ long long g_halo_t[148 * 8];  // one copy per translation unit
 
 namespace {
 
-constexpr int kHaloThreads = 320;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps2-9: epilogue (two per TMEM lane quarter)
+#ifndef REFID_HALO_EPI_WARPS
+#define REFID_HALO_EPI_WARPS 8
+#endif
+constexpr int kHaloEpiWarps = REFID_HALO_EPI_WARPS;  // 8 or 16: two or four epilogue warps per TMEM lane quarter
+constexpr int kHaloEpiSplit = kHaloEpiWarps / 4;     // 32-channel groups of a quarter are dealt round-robin to its warps
+constexpr int kHaloThreads = 64 + 32 * kHaloEpiWarps;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, then the epilogue warps
 constexpr int kHaloMaxStages = 8;
 
 // ---- epilogue with register prefetch --------------------------------------------------------------------------------
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);
+      mbar_init(&acc_empty[s], kHaloEpiWarps);
     }
     mbar_init(wres_bar, 1);
     fence_barrier_init();
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
             const int y02 = ((tile2 / p.tiles_x) % p.tiles_y) * (16 * NM);
             const int n2 = tile2 / tiles_per_img;
 #pragma unroll 1
-            for (int g = hsel; g < G; g += 2) {
+            for (int g = hsel; g < G; g += kHaloEpiSplit) {
               const int j = g / GPT, c0 = (g % GPT) * 32;
               const int y2 = y02 + j * 16 + ty;
               if (y2 >= p.H || x2 >= p.W) continue;
@@ -617,22 +622,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
         // the global operands do not depend on the accumulator: the first TWO groups are requested before the
         // accumulator-ready wait, every later group two groups ahead of its use
         if (INPUTS && hsel < G) prefetch(hsel, fa);
-        if (INPUTS && hsel + 2 < G) prefetch(hsel + 2, fb);
+        if (INPUTS && hsel + kHaloEpiSplit < G) prefetch(hsel + kHaloEpiSplit, fb);
         mbar_wait(&acc_full[buf], (it >> 1) & 1, 0x760 + buf);
         tc_fence_after();
         if (INPUTS) {
 #pragma unroll 1
-          for (int g = hsel; g < G; g += 4) {
+          for (int g = hsel; g < G; g += 2 * kHaloEpiSplit) {
             process(g, fa);
-            if (g + 4 < G) prefetch(g + 4, fa);
-            if (g + 2 < G) {
-              process(g + 2, fb);
-              if (g + 6 < G) prefetch(g + 6, fb);
+            if (g + 2 * kHaloEpiSplit < G) prefetch(g + 2 * kHaloEpiSplit, fa);
+            if (g + kHaloEpiSplit < G) {
+              process(g + kHaloEpiSplit, fb);
+              if (g + 3 * kHaloEpiSplit < G) prefetch(g + 3 * kHaloEpiSplit, fb);
             }
           }
         } else {
 #pragma unroll 1
-          for (int g = hsel; g < G; g += 2) process(g, fa);
+          for (int g = hsel; g < G; g += kHaloEpiSplit) process(g, fa);
         }
         tc_fence_before();
         __syncwarp();

@@ -54,6 +54,12 @@ def bench(cin, cout, H, W, N, cin2=0, pre=False, reps=20, sv=False):
     print(f"cin {cin}+{cin2} cout {cout} {N}x{H}x{W} pre={pre} sv={sv}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF/s  (device time, CUDA-graph replay)", flush=True)
 
 print("REFID_EPI_L2PF =", os.environ.get("REFID_EPI_L2PF"))
+if os.environ.get("CONV_BENCH_ONLY") == "enc0":
+    bench(32, 128, 256, 256, 8)     # enc0_in: both directions' level-0 in-convs stacked (one step's worth of the all-T launch)
+    bench(32, 128, 256, 256, 32)
+    bench(32, 64, 256, 256, 8)
+    bench(64, 128, 256, 256, 8)
+    sys.exit(0)
 bench(64, 64, 256, 256, 8)
 bench(64, 64, 256, 256, 8, pre=True)
 bench(64, 64, 256, 256, 8, pre=True, sv=True)
