@@ -241,7 +241,10 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
 // so the single issuing thread has <= 62 cycles per MMA at N <= 128.  The producer and MMA warps therefore run their
 // loops warp-uniformly (warp index via shuffle, elect.sync only around the issue) so that descriptors live in uniform
 // registers, and every per-MMA descriptor is `base + compile-time constant` (TAPS / pitch / NM are template parameters).
-template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16, bool LEAN>
+// SINGLE (LEAN kernels only): the launch has ONE EpiDesc, so every descriptor field is an immediate constant-bank operand and
+// the per-pixel address arithmetic is loop-invariant; a dynamically indexed descriptor costs a constant load (LDC, tens of
+// cycles) in front of every field test of every 32-channel group.
+template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16, bool LEAN, bool SINGLE = false>
 __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int PITCH = TAPS == 9 ? 10 : 8;       // pixels per patch row in shared memory
@@ -558,7 +561,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
           y = y0 + j * 16 + ty;
           valid = (y < p.H) && (x < p.W);
           const int ch = nblk * BN + c0;
-          e = &p.epi[ch >> p.epi_shift];
+          if constexpr (SINGLE) e = &p.epi[0];
+          else e = &p.epi[ch >> p.epi_shift];
           cseg = ch & epi_mask;
           pix = ((size_t)n * e->OH + (size_t)(y * e->osy + e->ooy)) * e->OW + (size_t)(x * e->osx + e->oox);
           off = pix * (size_t)e->C + e->coff + cseg;
@@ -672,11 +676,11 @@ inline size_t halo_smem_bytes(const HaloConvParams& p, int BN) {
 }
 
 
-template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16, bool LEAN>
+template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16, bool LEAN, bool SINGLE = false>
 int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
+    REFID_CUDA_CHECK(cudaFuncSetAttribute(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHaloSmemMax));
     configured = true;
   }
   static int num_sms = 0;
@@ -686,7 +690,7 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
     REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  REFID_CUDA_CHECK(launch_k(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN>, dim3(grid), dim3(kHaloThreads), halo_smem_bytes(p, BN), stream, p));
+  REFID_CUDA_CHECK(launch_k(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN, SINGLE>, dim3(grid), dim3(kHaloThreads), halo_smem_bytes(p, BN), stream, p));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -709,6 +713,8 @@ int launch_haloconv_flavour(const HaloConvParams& p, int BN, int NM, cudaStream_
     const EpiDesc& e = p.epi[i];
     if (e.out_nchw || e.out_f32 || e.pre2 || e.sv || e.post || e.out2 || e.out_pre || (e.act != ACT_NONE && e.act != ACT_LRELU)) lean = false;
   }
+  static const int no_single = getenv("REFID_NO_SINGLE") ? 1 : 0;
+  const bool single = !no_single && p.n_blocks * (BN >> p.epi_shift) == 1;
   static const int census = getenv("REFID_EPI_CENSUS") ? 1 : 0;  // diagnostic: which epilogue features launches use
   if (census) {
     unsigned f = 0;
@@ -723,10 +729,17 @@ int launch_haloconv_flavour(const HaloConvParams& p, int BN, int NM, cudaStream_
 #define HPICK(bn, nm, taps, kc, gl) \
   return in ? launch_halo_inst<bn, nm, taps, kc, gl, true, F16, false>(p, stream) : launch_halo_inst<bn, nm, taps, kc, gl, false, F16, false>(p, stream)
 #define HPICK9(bn, nm, taps, kc)                                                                                             \
-  return lean ? (in ? launch_halo_inst<bn, nm, taps, kc, false, true, F16, true>(p, stream)                                   \
-                    : launch_halo_inst<bn, nm, taps, kc, false, false, F16, true>(p, stream))                                 \
-              : (in ? launch_halo_inst<bn, nm, taps, kc, false, true, F16, false>(p, stream)                                  \
-                    : launch_halo_inst<bn, nm, taps, kc, false, false, F16, false>(p, stream))
+  {                                                                                                                          \
+    if constexpr (taps == 9) {                                                                                               \
+      if (lean && single)                                                                                                    \
+        return in ? launch_halo_inst<bn, nm, taps, kc, false, true, F16, true, true>(p, stream)                               \
+                  : launch_halo_inst<bn, nm, taps, kc, false, false, F16, true, true>(p, stream);                             \
+    }                                                                                                                        \
+    return lean ? (in ? launch_halo_inst<bn, nm, taps, kc, false, true, F16, true>(p, stream)                                 \
+                      : launch_halo_inst<bn, nm, taps, kc, false, false, F16, true>(p, stream))                               \
+                : (in ? launch_halo_inst<bn, nm, taps, kc, false, true, F16, false>(p, stream)                                \
+                      : launch_halo_inst<bn, nm, taps, kc, false, false, F16, false>(p, stream));                             \
+  }
 #define HINST(bn, nm)                                \
   if (BN == bn && NM == nm && p.kc == 64) {         \
     if (p.num_taps == 9) HPICK9(bn, nm, 9, 64);      \
