@@ -46,6 +46,10 @@ struct HaloConvParams {
   int bias_images;  // > 0: the bias table holds one row per image (EpiDesc::bias_nstride), bias_images = N
   int epi_l2pf;     // epilogue warps L2-prefetch the next item's global operands
   int f32_rmw;      // diagnostic: fp32 accumulation targets by read-modify-write instead of vector reductions
+  // Tail splitting (two-block tiles, NM == 2): the persistent CTAs process `full_items` whole items (a multiple of the grid)
+  // and then the remaining items as HALF items (one 16-row block each) -- when the remainder is at most half a round, the
+  // last round costs half: 512 tiles on 148 SMs take 3.5 instead of 4 rounds.  0: off.
+  int tail_split, full_items;
 };
 
 // Largest per-sample bias table (one row of n_blocks*BN floats per image) a launch may keep in shared memory.  REFID_BIAS_KB

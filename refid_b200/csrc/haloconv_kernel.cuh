@@ -244,6 +244,25 @@ __device__ __forceinline__ void epi_math32(const EpiDesc& e, float* v, float* v2
 // SINGLE (LEAN kernels only): the launch has ONE EpiDesc, so every descriptor field is an immediate constant-bank operand and
 // the per-pixel address arithmetic is loop-invariant; a dynamically indexed descriptor costs a constant load (LDC, tens of
 // cycles) in front of every field test of every 32-channel group.
+// Work unit w of a CTA's round-robin sequence -> (item, first 16-row block, number of blocks).  Whole items first; with tail
+// splitting the remainder comes as half items (see HaloConvParams::tail_split).
+template <int NM>
+__device__ __forceinline__ void halo_work(const HaloConvParams& p, int w, int& item, int& j0, int& nm_eff) {
+  if (NM == 1 || !p.tail_split || w < p.full_items) {
+    item = w;
+    j0 = 0;
+    nm_eff = NM;
+  } else {
+    const int sub = w - p.full_items;
+    item = p.full_items + sub / NM;
+    j0 = sub % NM;
+    nm_eff = 1;
+  }
+}
+__device__ __forceinline__ int halo_work_count(const HaloConvParams& p, int NM) {
+  return (NM > 1 && p.tail_split) ? p.full_items + (p.num_items - p.full_items) * NM : p.num_items;
+}
+
 template <int BN, int NM, int TAPS, int KC, bool GELU, bool INPUTS, bool F16, bool LEAN, bool SINGLE = false>
 __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_constant__ HaloConvParams p) {
   constexpr int HALO = TAPS == 9 ? 1 : 0;
@@ -338,10 +357,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
       }
     }
     RingPos ra, rb;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    const int nwork = halo_work_count(p, NM);
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+      int item, j0, nm_eff;
+      halo_work<NM>(p, w, item, j0, nm_eff);
       const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
       const int x0 = (tile % p.tiles_x) * 8;
-      const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
+      const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM) + j0 * 16;  // (a half item loads the whole patch box from its own first row)
       const int n = tile / tiles_per_img;
       int ks = 0;
       for (int src = 0; src < p.nsrc; ++src) {
@@ -384,7 +406,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
     RingPos ra, rb;
     uint32_t it = 0;
     HT_DECL;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+    const int nwork = halo_work_count(p, NM);
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+      int item, j0, nm_eff;
+      halo_work<NM>(p, w, item, j0, nm_eff);
       const uint32_t buf = it & 1;
       const int nblk_i = p.n_blocks == 1 ? 0 : item % p.n_blocks;
       const unsigned nmask = p.tap_mask[nblk_i] ? p.tap_mask[nblk_i] : 0xFFFFu;
@@ -414,6 +439,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
+                if (j >= nm_eff) continue;
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
                   const uint64_t ad = a_desc + (uint64_t)(((uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
@@ -436,6 +462,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
               const uint32_t tap_off = (uint32_t)(((TAPS == 9 ? tap / 3 : 0)) * PITCH + (TAPS == 9 ? tap % 3 : 0)) * PXB;
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
+                if (j >= nm_eff) continue;
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
                   const uint64_t ad = a_desc0 + (uint64_t)((tap_off + (uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
@@ -477,6 +504,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
                 const uint32_t tap_off = (uint32_t)(row * PITCH + q) * PXB;
 #pragma unroll
                 for (int j = 0; j < NM; ++j) {
+                  if (j >= nm_eff) continue;
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k) {
                     const uint64_t ad = a_desc0 + (uint64_t)((tap_off + (uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
@@ -509,6 +537,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
+                if (j >= nm_eff) continue;
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
                   const uint64_t ad = a_desc + (uint64_t)(((uint32_t)j * 16u * SBO + (uint32_t)k * 32u) >> 4);
@@ -550,16 +579,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) haloconv_kernel(const __grid_
       //      prefetched one group ahead into registers, 256-bit global accesses ----
       const int hsel = (warp - 2) >> 2;
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int nwork = halo_work_count(p, NM);
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+        int item, j0, nm_eff;
+        halo_work<NM>(p, w, item, j0, nm_eff);
         const int nblk = item % p.n_blocks, tile = item / p.n_blocks;
         const int x = (tile % p.tiles_x) * 8 + tx;
-        const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM);
+        const int y0 = ((tile / p.tiles_x) % p.tiles_y) * (16 * NM) + j0 * 16;
         const int n = tile / tiles_per_img;
         const uint32_t buf = it & 1;
         auto group_ctx = [&](int g, const EpiDesc*& e, size_t& off, size_t& pix, int& cword, int& cseg, int& y, bool& valid) {
           const int j = g / GPT, c0 = (g % GPT) * 32;
           y = y0 + j * 16 + ty;
-          valid = (y < p.H) && (x < p.W);
+          valid = (j < nm_eff) && (y < p.H) && (x < p.W);
           const int ch = nblk * BN + c0;
           if constexpr (SINGLE) e = &p.epi[0];
           else e = &p.epi[ch >> p.epi_shift];
@@ -690,6 +722,16 @@ int launch_halo_inst(const HaloConvParams& p, cudaStream_t stream) {
     REFID_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  static const int no_split = getenv("REFID_NO_TAIL_SPLIT") ? 1 : 0;
+  const int full = (p.num_items / grid) * grid, rem = p.num_items - full;
+  if (NM == 2 && !no_split && rem > 0 && rem * NM <= grid && !p.epi_l2pf) {
+    HaloConvParams q = p;
+    q.tail_split = 1;
+    q.full_items = full;
+    REFID_CUDA_CHECK(launch_k(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN, SINGLE>, dim3(grid), dim3(kHaloThreads), halo_smem_bytes(p, BN), stream, q));
+    REFID_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   REFID_CUDA_CHECK(launch_k(haloconv_kernel<BN, NM, TAPS, KC, GELU, INPUTS, F16, LEAN, SINGLE>, dim3(grid), dim3(kHaloThreads), halo_smem_bytes(p, BN), stream, p));
   REFID_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -236,6 +236,13 @@ CASES = {
     "conv3x3_256_256_pair": lambda: case_conv3x3(cin=256, cout=256, H=32, W=40, N=2),
     "conv3x3_256_256_h4": lambda: case_conv3x3(cin=256, cout=256, H=4, W=4, N=3),
     "conv3x3_ragged_24x20": lambda: case_conv3x3(H=24, W=20, N=1),
+    # 168 two-block items on 148 SMs: the 20 items of the last round run as 40 half items (tail splitting, haloconv.cuh)
+    "conv3x3_64_64_tail_split": lambda: case_conv3x3(H=128, W=112, N=3),
+    "conv3x3_64_64_tail_split_ragged_pre": lambda: case_conv3x3(H=120, W=108, N=3, pre=True),
+    "conv3x3_128_128_tail_split_streamed": lambda: case_conv3x3(cin=128, cout=128, H=128, W=112, N=3, pre=True),
+    "conv3x3_dual_64+64_64_tail_split": lambda: case_conv3x3(cin2=64, H=120, W=112, N=3),
+    "conv3x3_32_32_tail_split": lambda: case_conv3x3(cin=32, cout=32, H=128, W=112, N=3),
+    "dgrad3x3_split_tail_split": lambda: case_dgrad3x3_split(N=3, H=128, W=112),
     "conv3x3_64_64_gelu": lambda: case_conv3x3(act=ACT_GELU),
     "dgrad3x3_split": lambda: case_dgrad3x3_split(),
     "conv1x1_128_64_gelu_post": lambda: case_conv1x1(),
