@@ -96,6 +96,7 @@ struct ConvOp {
   bool defer_in1 = false;  // in[1] is the same tensor at every step: its gradient is computed once from the summed dL/dZ
   bool rep_in1 = false;    // in[1] has fewer images than in[0] and repeats along the image axis (chunk ops; implies defer_in1)
   bool post_no_grad = false;  // the skip-sum addend's gradient is handed over elsewhere (once for all T steps)
+  bool out2_grad_preadded = false;  // out2's gradient was registered as a pending addend of `out` before this level's backward
 };
 
 typedef std::function<int(cudaStream_t)> Launch;
@@ -876,7 +877,7 @@ struct Engine {
       if (gs) {
         const int g = tens[op.out2].gidx;
         const long go = tens[op.out2].goff;
-        add_pending(op.out, g, go);
+        if (!op.out2_grad_preadded) add_pending(op.out, g, go);
         if (!op.post_no_grad) add_pending(op.post, g, go);
       }
       release_grad(op.out2);
@@ -1390,7 +1391,7 @@ struct Engine {
   }
 
   int trunk(const std::string& p, int u, int hprev, const std::string& nm, int post, int out2_preset, int* out2,
-            int h_preset = -1, bool post_no_grad = false) {
+            int h_preset = -1, bool post_no_grad = false, bool out2_grad_preadded = false) {
     ConvOp a;
     a.site = site(p + ".main.0");
     a.in[0] = u;
@@ -1413,6 +1414,7 @@ struct Engine {
     c.res = v;
     c.post = post;
     c.post_no_grad = post_no_grad;
+    c.out2_grad_preadded = out2_grad_preadded;
     c.out2 = out2_preset;
     c.out = h_preset;
     const int h = conv(c, nm + ".h");
@@ -1830,6 +1832,9 @@ struct Engine {
           return 0;
         });
       }
+      std::vector<std::pair<int, int>> pre_pairs;  // (decoder state of step t, step view of the level's all-T skip-sum output)
+      static const bool no_preadd = getenv("REFID_NO_PREADD") != nullptr;  // diagnostic
+      const bool preadd = train && !no_preadd;
       for (auto& ck : so.chunks) {
         const int t0 = ck.first, k = ck.second, n0 = t0 * B, nk = k * B;
         ConvOp up;
@@ -1848,7 +1853,8 @@ struct Engine {
           const int preset = view(o2_all, t * B, B, 0, Cd);
           int o2 = -1;
           const int hs = series_tensor(sd_series[i], t + 1, B, Hd, Wd, Cd);
-          const int st = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2, hs, i == 2);
+          const int st = trunk(p + ".forward_trunk", u, sd[i], nm, post, preset, &o2, hs, i == 2, preadd);
+          if (preadd && st >= 0) pre_pairs.push_back({st, preset});
           if (st < 0) {
             cur_slot = -1;
             return 1;
@@ -1868,6 +1874,25 @@ struct Engine {
           cp.nchw_tstride = (long)cfg.out_chn * H * W;
           conv(cp);
         }
+      }
+      if (preadd) {
+        // The gradient of the skip-sum output of every step (a slice of ONE all-T buffer, written by the next level's chunk
+        // ops / `pred` before this level is back-propagated) also is a gradient of that step's decoder state.  Registered
+        // here -- the first thing this level's backward does --, it rides as the epilogue addend of the NEXT step's main.0
+        // data-gradient (which writes dL/ds_t) instead of costing one masked-accumulate pass per step and level afterwards.
+        Engine* self = this;
+        tape.push_back([self, pre_pairs]() {
+          for (auto& pr : pre_pairs) {
+            const int v = pr.second, par = self->tens[v].parent;
+            if (par < 0 || !(self->tens[par].gwritten || self->tens[par].goff >= 0)) {
+              set_error("decoder skip-sum gradient is not available before its level's backward");
+              return 1;
+            }
+            self->ensure_gbuf(v);
+            if (self->add_pending(pr.first, self->tens[v].gidx, self->tens[v].goff)) return 1;
+          }
+          return 0;
+        });
       }
       in_all = o2_all;
     }
