@@ -193,7 +193,16 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
     for (int g = 0; g < ngroups; ++g) const_cast<OutGroup*>(groups)[g].epi.sv_bits = nullptr;
   // preference: resident weights (two pixel tiles per item, else one) before streamed weights -- re-streaming the
   // weights of a C=64 dual-source conv per 256-pixel item costs more than the smaller M (measured 111 vs 83 us MMA-side)
-  const int nm_pref = (2 * 2 * BN <= 512 && GH > 16) ? 2 : 1;
+  int nm_pref = (2 * 2 * BN <= 512 && GH > 16) ? 2 : 1;
+  {
+    // small grids (the reference's own batch of 1 per GPU): when two-block tiles would occupy at most half of the SMs,
+    // one-block tiles double the number of busy SMs for the same work
+    static const int no_small = getenv("REFID_NO_SMALL_TILES") ? 1 : 0;
+    static int sms = 0;
+    if (!sms && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess || sms <= 0)) sms = 148;
+    const long items2 = (long)((GW + 7) / 8) * ((GH + 31) / 32) * d.N * h.n_blocks;
+    if (!no_small && nm_pref == 2 && items2 * 2 <= sms) nm_pref = 1;
+  }
   int NM = 0;
   if (haloconv_plan(&h, BN, nm_pref, 1)) NM = nm_pref;
   else if (haloconv_plan(&h, BN, 1, 1)) NM = 1;
