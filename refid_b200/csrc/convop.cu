@@ -119,6 +119,18 @@ static int try_build_halo(const ConvDesc& d, const OutGroup* groups, int ngroups
   int BN = kc == 64 ? 256 : 128;
   while (BN > 32 && total % BN) BN >>= 1;
   if (total % BN) return 0;
+  {
+    // small grids: a narrower N tile while the launch would otherwise occupy at most half of the SMs (same total weight
+    // stream, twice the busy SMs); never below 64 output channels per tile (N = 32 MMAs run at a third of the rate)
+    static const int no_small = getenv("REFID_NO_SMALL_TILES") ? 1 : 0;
+    static int sms = 0;
+    if (!sms && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess || sms <= 0)) sms = 148;
+    auto items_for = [&](int bn) {
+      const int nm = (2 * 2 * bn <= 512 && GH > 16) ? 2 : 1;
+      return (long)((GW + 7) / 8) * ((GH + 16 * nm - 1) / (16 * nm)) * d.N * (total / bn) * (scatter4 ? 4 : 1);
+    };
+    while (!no_small && kc == 64 && BN > 64 && items_for(BN) * 2 <= sms && (scatter4 ? 4 : 1) * (total / (BN / 2)) <= kMaxNBlocks) BN >>= 1;
+  }
   if (seg > BN) seg = BN;
   if (BN % seg || (total / seg) > kMaxNBlocks) return 0;
   HaloConvParams& h = out->hp;
